@@ -1,0 +1,100 @@
+// Host-side rating files behind the mfb_blocks_* entry points (no GPU involved).
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "mfb_internal.h"
+#include "proto_wire.h"
+
+struct mfb_blocks {
+  mfb::Dataset d;  // host staging arrays only
+};
+
+using namespace mfb;
+
+namespace mfb {
+const Dataset* blocks_data(const mfb_blocks* b) { return &b->d; }
+mfb_blocks* blocks_new() {
+  mfb_blocks* b = new mfb_blocks();
+  b->d.h_run_off.push_back(0);
+  b->d.h_block_off.push_back(0);
+  return b;
+}
+Dataset* blocks_mut(mfb_blocks* b) { return &b->d; }
+}  // namespace mfb
+
+extern "C" {
+
+int mfb_blocks_read(const char* path, mfb_blocks** out) {
+  MFB_REQUIRE(path && out, "NULL argument");
+  mfb_blocks* b = blocks_new();
+  int rc = load_blocks_file(path, &b->d);
+  if (rc) {
+    delete b;
+    *out = nullptr;
+    return rc;
+  }
+  *out = b;
+  return MFB_OK;
+}
+
+int mfb_blocks_from_arrays(int64_t nblocks, const int64_t* block_off, int64_t nruns,
+                           const int32_t* run_uid, const int32_t* run_off, const int32_t* vid,
+                           const float* rating, mfb_blocks** out) {
+  MFB_REQUIRE(out && block_off && run_off && nblocks >= 0 && nruns >= 0, "bad argument");
+  MFB_REQUIRE(block_off[0] == 0 && block_off[nblocks] == nruns, "block_off must span [0,nruns]");
+  mfb_blocks* b = new mfb_blocks();
+  const int64_t n = nruns ? run_off[nruns] : 0;
+  b->d.h_block_off.assign(block_off, block_off + nblocks + 1);
+  b->d.h_run_uid.assign(run_uid, run_uid + nruns);
+  b->d.h_run_off.assign(run_off, run_off + nruns + 1);
+  b->d.h_vid.assign(vid, vid + n);
+  b->d.h_rating.assign(rating, rating + n);
+  *out = b;
+  return MFB_OK;
+}
+
+int mfb_blocks_write(const mfb_blocks* b, const char* path) {
+  MFB_REQUIRE(b && path, "NULL argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    set_error("cannot create %s", path);
+    return MFB_E_IO;
+  }
+  const Dataset& d = b->d;
+  std::string buf;
+  std::vector<int32_t> rec_off;
+  const int64_t nblocks = (int64_t)d.h_block_off.size() - 1;
+  for (int64_t k = 0; k < nblocks; k++) {
+    const int64_t r0 = d.h_block_off[k], r1 = d.h_block_off[k + 1];
+    const int32_t base = d.h_run_off[r0];
+    rec_off.resize(r1 - r0 + 1);
+    for (int64_t r = r0; r <= r1; r++) rec_off[r - r0] = d.h_run_off[r] - base;
+    encode_block((int32_t)(r1 - r0), d.h_run_uid.data() + r0, rec_off.data(), d.h_vid.data() + base,
+                 d.h_rating.data() + base, &buf);
+    const uint32_t sz = (uint32_t)buf.size();  // getdata.cc:100-103
+    if (fwrite(&sz, 1, 4, f) != 4 || fwrite(buf.data(), 1, sz, f) != sz) {
+      fclose(f);
+      set_error("short write to %s", path);
+      return MFB_E_IO;
+    }
+  }
+  if (fclose(f) != 0) {
+    set_error("close failed on %s", path);
+    return MFB_E_IO;
+  }
+  return MFB_OK;
+}
+
+void mfb_blocks_free(mfb_blocks* b) { delete b; }
+int64_t mfb_blocks_num_blocks(const mfb_blocks* b) { return b ? (int64_t)b->d.h_block_off.size() - 1 : -1; }
+int64_t mfb_blocks_num_runs(const mfb_blocks* b) { return b ? (int64_t)b->d.h_run_uid.size() : -1; }
+int64_t mfb_blocks_num_ratings(const mfb_blocks* b) { return b ? (int64_t)b->d.h_vid.size() : -1; }
+const int64_t* mfb_blocks_block_off(const mfb_blocks* b) { return b->d.h_block_off.data(); }
+const int32_t* mfb_blocks_run_uid(const mfb_blocks* b) { return b->d.h_run_uid.data(); }
+const int32_t* mfb_blocks_run_off(const mfb_blocks* b) { return b->d.h_run_off.data(); }
+const int32_t* mfb_blocks_vid(const mfb_blocks* b) { return b->d.h_vid.data(); }
+const float* mfb_blocks_rating(const mfb_blocks* b) { return b->d.h_rating.data(); }
+
+}  // extern "C"

@@ -1,0 +1,535 @@
+// C-ABI entry points of include/mf_b200.h: context, factor access, datasets, epoch drivers.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "mfb_internal.h"
+
+namespace mfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int64_t array_rows(const Context* c, int which) {
+  switch (which) {
+    case MFB_THETA: case MFB_THETA_OLD: case MFB_BU: case MFB_BU_OLD: case MFB_UR: return c->nu;
+    case MFB_PHI: case MFB_PHI_OLD: case MFB_BV: case MFB_BV_OLD: case MFB_VR: return c->nv;
+    case MFB_LAMBDA_U: case MFB_LAMBDA_V: return c->dim;
+    default: return 0;
+  }
+}
+int array_cols(const Context* c, int which) {
+  switch (which) {
+    case MFB_THETA: case MFB_THETA_OLD: case MFB_PHI: case MFB_PHI_OLD: return c->dim;
+    default: return 1;
+  }
+}
+int array_stride(const Context* c, int which) {
+  switch (which) {
+    case MFB_THETA: case MFB_THETA_OLD: case MFB_PHI: case MFB_PHI_OLD: return c->stride;
+    default: return 1;
+  }
+}
+
+static int alloc_array(Context* c, int which) {
+  if (c->arr[which]) return MFB_OK;
+  size_t n = (size_t)array_rows(c, which) * array_stride(c, which);
+  if (which == MFB_LAMBDA_U || which == MFB_LAMBDA_V) n = (size_t)c->stride;  // padded with zeros
+  if (n == 0) n = 1;
+  MFB_CUDA(cudaMalloc(&c->arr[which], n * sizeof(float)));
+  MFB_CUDA(cudaMemsetAsync(c->arr[which], 0, n * sizeof(float), c->stream));
+  return MFB_OK;
+}
+
+static Dataset* get_ds(Context* c, int ds) {
+  if (ds < 0 || ds >= (int)c->datasets.size() || !c->datasets[ds].used) {
+    set_error("bad dataset id %d", ds);
+    return nullptr;
+  }
+  return &c->datasets[ds];
+}
+
+static void free_ds_device(Dataset* d) {
+  cudaFree(d->d_run_uid); cudaFree(d->d_run_off); cudaFree(d->d_vid); cudaFree(d->d_rating);
+  cudaFree(d->d_uc); cudaFree(d->d_vc); cudaFree(d->d_last_u); cudaFree(d->d_last_v);
+  d->d_run_uid = d->d_run_off = d->d_vid = nullptr;
+  d->d_rating = nullptr;
+  d->d_uc = d->d_vc = d->d_last_u = d->d_last_v = nullptr;
+}
+
+static void begin_timing(Context* c) {
+  cudaEventRecord(c->ev0, c->stream);
+}
+static void end_timing(Context* c) {
+  cudaEventRecord(c->ev1, c->stream);
+  c->timed = true;
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+static int append_host(Context* c, Dataset* d, const Dataset& src) {
+  if (d->h_run_off.empty()) d->h_run_off.push_back(0);
+  if (d->h_block_off.empty()) d->h_block_off.push_back(0);
+  const int64_t base = (int64_t)d->h_vid.size(), rbase = (int64_t)d->h_run_uid.size();
+  MFB_REQUIRE(base + (int64_t)src.h_vid.size() < (int64_t)INT32_MAX, "dataset too large for int32 offsets");
+  for (int32_t u : src.h_run_uid) MFB_REQUIRE(u >= 0 && u < c->nu, "uid %d outside [0,%d)", u, c->nu);
+  for (int32_t v : src.h_vid) MFB_REQUIRE(v >= 0 && v < c->nv, "vid %d outside [0,%d)", v, c->nv);
+  d->h_run_uid.insert(d->h_run_uid.end(), src.h_run_uid.begin(), src.h_run_uid.end());
+  for (size_t r = 1; r < src.h_run_off.size(); r++) d->h_run_off.push_back((int32_t)(base + src.h_run_off[r]));
+  d->h_vid.insert(d->h_vid.end(), src.h_vid.begin(), src.h_vid.end());
+  d->h_rating.insert(d->h_rating.end(), src.h_rating.begin(), src.h_rating.end());
+  for (size_t b = 1; b < src.h_block_off.size(); b++) d->h_block_off.push_back(rbase + src.h_block_off[b]);
+  return MFB_OK;
+}
+
+template <typename T>
+static int to_device(Context* c, const std::vector<T>& hv, T** dp) {
+  size_t bytes = std::max<size_t>(hv.size(), 1) * sizeof(T);
+  MFB_CUDA(cudaMalloc(dp, bytes));
+  if (!hv.empty())
+    MFB_CUDA(cudaMemcpyAsync(*dp, hv.data(), hv.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return MFB_OK;
+}
+
+template <typename T>
+static void release(std::vector<T>& v) {
+  std::vector<T>().swap(v);
+}
+
+extern "C" {
+
+const char* mfb_last_error(void) { return g_err; }
+const char* mfb_version(void) { return "0.1 sm_100a"; }
+
+// util.h:163-165 with CACHE_LINE_SIZE 64: round the row up to a multiple of 16 floats
+int mfb_padding(int dim) {
+  return (int)((((size_t)dim * sizeof(float) - 1) / 64 * 64 + 64) / sizeof(float));
+}
+
+float mfb_seteta(float eta0, int round, float gam) {  // model.cc:36-38
+  return (float)((double)eta0 * 1.0 / pow((double)round, (double)gam));
+}
+float mfb_seteta_cutoff(float eta0, int round, float gam, float mineta) {  // model.cc:350-352
+  const float e = mfb_seteta(eta0, round, gam);
+  return mineta > e ? mineta : e;
+}
+
+int mfb_create(mfb_ctx** out, int device, int nu, int nv, int dim) {
+  MFB_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  MFB_REQUIRE(nu > 0 && nv > 0 && dim > 0 && dim <= 2048, "bad shape nu=%d nv=%d dim=%d", nu, nv, dim);
+  int ndev = 0;
+  MFB_CUDA(cudaGetDeviceCount(&ndev));
+  MFB_REQUIRE(device >= 0 && device < ndev, "device %d of %d", device, ndev);
+  MFB_CUDA(cudaSetDevice(device));
+  mfb_ctx* h = new mfb_ctx();
+  Context* c = &h->c;
+  c->device = device;
+  c->nu = nu;
+  c->nv = nv;
+  c->dim = dim;
+  c->stride = mfb_padding(dim);
+  cudaDeviceProp prop;
+  MFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  MFB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  MFB_CUDA(cudaEventCreate(&c->ev0));
+  MFB_CUDA(cudaEventCreate(&c->ev1));
+  MFB_CUDA(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
+  MFB_CUDA(cudaMalloc(&c->d_accum, 8 * sizeof(double)));
+  MFB_CUDA(cudaMallocHost(&c->h_accum, 8 * sizeof(double)));
+  for (int w : {MFB_THETA, MFB_PHI, MFB_BU, MFB_BV}) {
+    int rc = alloc_array(c, w);
+    if (rc) return rc;
+  }
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  *out = h;
+  return MFB_OK;
+}
+
+void mfb_destroy(mfb_ctx* h) {
+  if (!h) return;
+  Context* c = &h->c;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& d : c->datasets) free_ds_device(&d);
+  for (auto& p : c->arr) cudaFree(p);
+  cudaFree(c->d_counter);
+  cudaFree(c->d_accum);
+  cudaFreeHost(c->h_accum);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto e : c->chunk_events) cudaEventDestroy(e);
+  delete h;
+}
+
+int mfb_set_stream(mfb_ctx* h, void* s) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return MFB_OK;
+}
+
+int mfb_sync(mfb_ctx* h) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  MFB_CUDA(cudaStreamSynchronize(h->c.stream));
+  return MFB_OK;
+}
+
+int mfb_set_option(mfb_ctx* h, const char* name, int value) {
+  MFB_REQUIRE(h && name, "NULL argument");
+  Context* c = &h->c;
+  if (!strcmp(name, "ctas_per_sm")) {
+    MFB_REQUIRE(value >= 0 && value <= 32, "ctas_per_sm out of range");
+    c->opt_ctas_per_sm = value;
+  } else if (!strcmp(name, "threads")) {
+    MFB_REQUIRE(value == 32 || value == 64 || value == 128 || value == 256, "threads must be 32/64/128/256");
+    c->opt_threads = value;
+  } else {
+    set_error("unknown option %s", name);
+    return MFB_E_ARG;
+  }
+  return MFB_OK;
+}
+
+int mfb_enable(mfb_ctx* h, int group) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (group == 1) {
+    for (int w : {MFB_THETA_OLD, MFB_PHI_OLD, MFB_BU_OLD, MFB_BV_OLD}) {
+      int rc = alloc_array(c, w);
+      if (rc) return rc;
+    }
+  } else if (group == 2) {
+    for (int w : {MFB_UR, MFB_VR, MFB_LAMBDA_U, MFB_LAMBDA_V}) {
+      int rc = alloc_array(c, w);
+      if (rc) return rc;
+    }
+  } else {
+    set_error("unknown array group %d", group);
+    return MFB_E_ARG;
+  }
+  return MFB_OK;
+}
+
+static int xfer(mfb_ctx* h, int which, float* host, int64_t row0, int64_t nrows, int64_t hs,
+                bool up) {
+  MFB_REQUIRE(h && host, "NULL argument");
+  Context* c = &h->c;
+  MFB_REQUIRE(which >= 0 && which < 12 && c->arr[which], "array %d not allocated", which);
+  const int64_t rows = array_rows(c, which);
+  const int cols = array_cols(c, which), ds = array_stride(c, which);
+  MFB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "rows [%lld,+%lld) outside 0..%lld",
+              (long long)row0, (long long)nrows, (long long)rows);
+  MFB_REQUIRE(hs >= cols, "host stride %lld < %d columns", (long long)hs, cols);
+  if (nrows == 0) return MFB_OK;
+  MFB_CUDA(cudaSetDevice(c->device));
+  float* dev = c->arr[which] + row0 * ds;
+  if (up)
+    MFB_CUDA(cudaMemcpy2DAsync(dev, ds * sizeof(float), host, hs * sizeof(float),
+                               cols * sizeof(float), nrows, cudaMemcpyHostToDevice, c->stream));
+  else
+    MFB_CUDA(cudaMemcpy2DAsync(host, hs * sizeof(float), dev, ds * sizeof(float),
+                               cols * sizeof(float), nrows, cudaMemcpyDeviceToHost, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  return MFB_OK;
+}
+
+int mfb_upload(mfb_ctx* h, int which, const float* host, int64_t row0, int64_t nrows, int64_t hs) {
+  return xfer(h, which, const_cast<float*>(host), row0, nrows, hs, true);
+}
+int mfb_download(mfb_ctx* h, int which, float* host, int64_t row0, int64_t nrows, int64_t hs) {
+  return xfer(h, which, host, row0, nrows, hs, false);
+}
+
+int mfb_init_normal(mfb_ctx* h, uint64_t seed, float scale) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  MFB_CUDA(cudaSetDevice(h->c.device));
+  return launch_fill_normal(&h->c, seed, scale);
+}
+
+int mfb_snapshot_old(mfb_ctx* h) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  MFB_REQUIRE(c->arr[MFB_THETA_OLD], "admf shadows not enabled");
+  const int src[4] = {MFB_THETA, MFB_PHI, MFB_BU, MFB_BV};
+  const int dst[4] = {MFB_THETA_OLD, MFB_PHI_OLD, MFB_BU_OLD, MFB_BV_OLD};
+  for (int i = 0; i < 4; i++) {
+    size_t n = (size_t)array_rows(c, src[i]) * array_stride(c, src[i]) * sizeof(float);
+    MFB_CUDA(cudaMemcpyAsync(c->arr[dst[i]], c->arr[src[i]], n, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return MFB_OK;
+}
+
+void* mfb_device_ptr(mfb_ctx* h, int which) {
+  if (!h || which < 0 || which >= 12) return nullptr;
+  return h->c.arr[which];
+}
+
+// ---- datasets ---------------------------------------------------------------------------------
+int mfb_dataset_create(mfb_ctx* h, int* ds) {
+  MFB_REQUIRE(h && ds, "NULL argument");
+  Context* c = &h->c;
+  for (size_t i = 0; i < c->datasets.size(); i++)
+    if (!c->datasets[i].used) {
+      c->datasets[i] = Dataset();
+      c->datasets[i].used = true;
+      *ds = (int)i;
+      return MFB_OK;
+    }
+  c->datasets.emplace_back();
+  c->datasets.back().used = true;
+  *ds = (int)c->datasets.size() - 1;
+  return MFB_OK;
+}
+
+int mfb_dataset_append_block(mfb_ctx* h, int ds, int32_t nusers, const int32_t* uid,
+                             const int32_t* rec_off, const int32_t* vid, const float* rating) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(!d->finalized, "dataset %d already finalized", ds);
+  MFB_REQUIRE(nusers >= 0 && (nusers == 0 || (uid && rec_off)), "bad block");
+  if (d->h_run_off.empty()) d->h_run_off.push_back(0);
+  if (d->h_block_off.empty()) d->h_block_off.push_back(0);
+  const int64_t base = (int64_t)d->h_vid.size();
+  const int64_t n = nusers ? rec_off[nusers] - rec_off[0] : 0;
+  MFB_REQUIRE(n >= 0 && base + n < (int64_t)INT32_MAX, "dataset too large for int32 offsets");
+  MFB_REQUIRE(n == 0 || (vid && rating), "NULL records");
+  for (int32_t i = 0; i < nusers; i++) {
+    MFB_REQUIRE(uid[i] >= 0 && uid[i] < c->nu, "uid %d outside [0,%d)", uid[i], c->nu);
+    MFB_REQUIRE(rec_off[i + 1] >= rec_off[i], "rec_off not monotone");
+    d->h_run_uid.push_back(uid[i]);
+    d->h_run_off.push_back((int32_t)(base + rec_off[i + 1] - rec_off[0]));
+  }
+  const int32_t* v0 = vid + (nusers ? rec_off[0] : 0);
+  for (int64_t k = 0; k < n; k++)
+    MFB_REQUIRE(v0[k] >= 0 && v0[k] < c->nv, "vid %d outside [0,%d)", v0[k], c->nv);
+  d->h_vid.insert(d->h_vid.end(), v0, v0 + n);
+  const float* r0 = rating + (nusers ? rec_off[0] : 0);
+  d->h_rating.insert(d->h_rating.end(), r0, r0 + n);
+  d->h_block_off.push_back((int64_t)d->h_run_uid.size());
+  return MFB_OK;
+}
+
+int mfb_dataset_append_blocks(mfb_ctx* h, int ds, const mfb_blocks* b) {
+  MFB_REQUIRE(h && b, "NULL argument");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(!d->finalized, "dataset %d already finalized", ds);
+  return append_host(c, d, *blocks_data(b));
+}
+
+int mfb_dataset_load_file(mfb_ctx* h, int ds, const char* path) {
+  MFB_REQUIRE(h && path, "NULL argument");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(!d->finalized, "dataset %d already finalized", ds);
+  int rc = load_blocks_file(path, d);
+  if (rc) return rc;
+  for (int32_t u : d->h_run_uid) MFB_REQUIRE(u >= 0 && u < c->nu, "uid %d outside [0,%d) in %s", u, c->nu, path);
+  for (int32_t v : d->h_vid) MFB_REQUIRE(v >= 0 && v < c->nv, "vid %d outside [0,%d) in %s", v, c->nv, path);
+  return MFB_OK;
+}
+
+int mfb_dataset_finalize(mfb_ctx* h, int ds) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(!d->finalized, "dataset %d already finalized", ds);
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (d->h_run_off.empty()) d->h_run_off.push_back(0);
+  if (d->h_block_off.empty()) d->h_block_off.push_back(0);
+  d->nruns = (int64_t)d->h_run_uid.size();
+  d->nratings = (int64_t)d->h_vid.size();
+  d->nblocks = (int64_t)d->h_block_off.size() - 1;
+  int rc;
+  if ((rc = to_device(c, d->h_run_uid, &d->d_run_uid))) return rc;
+  if ((rc = to_device(c, d->h_run_off, &d->d_run_off))) return rc;
+  if ((rc = to_device(c, d->h_vid, &d->d_vid))) return rc;
+  if ((rc = to_device(c, d->h_rating, &d->d_rating))) return rc;
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  // the tiles are resident in HBM; drop the host staging copies (keep the small run tables)
+  release(d->h_vid);
+  release(d->h_rating);
+  d->finalized = true;
+  return MFB_OK;
+}
+
+int mfb_dataset_free(mfb_ctx* h, int ds) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  cudaStreamSynchronize(c->stream);
+  free_ds_device(d);
+  *d = Dataset();
+  return MFB_OK;
+}
+
+int64_t mfb_dataset_num_ratings(mfb_ctx* h, int ds) {
+  Dataset* d = h ? get_ds(&h->c, ds) : nullptr;
+  return d ? (d->finalized ? d->nratings : (int64_t)d->h_vid.size()) : -1;
+}
+int64_t mfb_dataset_num_runs(mfb_ctx* h, int ds) {
+  Dataset* d = h ? get_ds(&h->c, ds) : nullptr;
+  return d ? (d->finalized ? d->nruns : (int64_t)d->h_run_uid.size()) : -1;
+}
+
+// ---- hot path -----------------------------------------------------------------------------------
+int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mode) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC,
+              "bad mode %d", mode);
+  MFB_CUDA(cudaSetDevice(c->device));
+  begin_timing(c);
+  int rc = d->nruns ? launch_sgd(c, d, eta, lambda, gb, mode, 0, d->nruns) : MFB_OK;
+  end_timing(c);
+  return rc;
+}
+
+// One epoch whose inputs start in HOST memory: the rating tiles of `src` are copied H2D chunk
+// by chunk on a second stream while the update kernel works on the previous chunk - the
+// reference's read -> parse -> update pipeline (main.cc:45-50) with PCIe as the "read" stage.
+int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta, float lambda,
+                            float gb, int mode, int64_t chunk_ratings) {
+  MFB_REQUIRE(h && src, "NULL argument");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  const Dataset* s = blocks_data(src);
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_REQUIRE((int64_t)s->h_run_uid.size() == d->nruns && (int64_t)s->h_vid.size() == d->nratings,
+              "host blocks (%zu runs, %zu ratings) do not match dataset %d (%lld, %lld)",
+              s->h_run_uid.size(), s->h_vid.size(), ds, (long long)d->nruns, (long long)d->nratings);
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC, "streamed epochs are Hogwild/atomic only");
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (chunk_ratings <= 0) chunk_ratings = 8 << 20;
+  begin_timing(c);
+  // the copy stream must not overwrite tiles that work queued earlier on the main stream still reads
+  cudaEvent_t start_ev;
+  if (c->chunk_events.empty()) {
+    cudaEvent_t e;
+    MFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->chunk_events.push_back(e);
+  }
+  start_ev = c->chunk_events[0];
+  MFB_CUDA(cudaEventRecord(start_ev, c->stream));
+  MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, start_ev, 0));
+  int64_t r0 = 0;
+  size_t chunk = 0;
+  while (r0 < d->nruns) {
+    int64_t r1 = r0;
+    const int64_t o0 = s->h_run_off[r0];
+    while (r1 < d->nruns && s->h_run_off[r1 + 1] - o0 <= chunk_ratings) r1++;
+    if (r1 == r0) r1 = r0 + 1;  // a single run longer than the chunk size
+    const int64_t o1 = s->h_run_off[r1];
+    MFB_CUDA(cudaMemcpyAsync(d->d_run_uid + r0, s->h_run_uid.data() + r0, (r1 - r0) * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(d->d_run_off + r0, s->h_run_off.data() + r0, (r1 - r0 + 1) * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(d->d_vid + o0, s->h_vid.data() + o0, (o1 - o0) * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(d->d_rating + o0, s->h_rating.data() + o0, (o1 - o0) * sizeof(float),
+                             cudaMemcpyHostToDevice, c->copy_stream));
+    ++chunk;
+    if (c->chunk_events.size() <= chunk) {
+      cudaEvent_t e;
+      MFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->chunk_events.push_back(e);
+    }
+    MFB_CUDA(cudaEventRecord(c->chunk_events[chunk], c->copy_stream));
+    MFB_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_events[chunk], 0));
+    int rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
+    if (rc) return rc;
+    r0 = r1;
+  }
+  end_timing(c);
+  return MFB_OK;
+}
+
+int mfb_blocks_pin(mfb_blocks* b) {
+  MFB_REQUIRE(b, "NULL argument");
+  Dataset* s = blocks_mut(b);
+  if (s->pinned) return MFB_OK;
+  auto reg = [](const void* p, size_t bytes) {
+    return bytes ? cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable) : cudaSuccess;
+  };
+  MFB_CUDA(reg(s->h_run_uid.data(), s->h_run_uid.size() * sizeof(int32_t)));
+  MFB_CUDA(reg(s->h_run_off.data(), s->h_run_off.size() * sizeof(int32_t)));
+  MFB_CUDA(reg(s->h_vid.data(), s->h_vid.size() * sizeof(int32_t)));
+  MFB_CUDA(reg(s->h_rating.data(), s->h_rating.size() * sizeof(float)));
+  s->pinned = true;
+  return MFB_OK;
+}
+
+int mfb_blocks_unpin(mfb_blocks* b) {
+  MFB_REQUIRE(b, "NULL argument");
+  Dataset* s = blocks_mut(b);
+  if (!s->pinned) return MFB_OK;
+  if (!s->h_run_uid.empty()) cudaHostUnregister(s->h_run_uid.data());
+  if (!s->h_run_off.empty()) cudaHostUnregister(s->h_run_off.data());
+  if (!s->h_vid.empty()) cudaHostUnregister(s->h_vid.data());
+  if (!s->h_rating.empty()) cudaHostUnregister(s->h_rating.data());
+  s->pinned = false;
+  return MFB_OK;
+}
+
+int mfb_sse(mfb_ctx* h, int ds, float gb, double* sse, int64_t* n) {
+  MFB_REQUIRE(h && sse, "NULL argument");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_CUDA(cudaSetDevice(c->device));
+  *sse = 0.0;
+  if (n) *n = d->nratings;
+  if (d->nruns == 0) return MFB_OK;
+  begin_timing(c);
+  int rc = launch_sse(c, d, gb);
+  end_timing(c);
+  if (rc) return rc;
+  MFB_CUDA(cudaMemcpyAsync(c->h_accum, c->d_accum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  *sse = c->h_accum[0];
+  return MFB_OK;
+}
+
+float mfb_last_kernel_ms(mfb_ctx* h) {
+  if (!h || !h->c.timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(h->c.ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, h->c.ev0, h->c.ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+int64_t mfb_launch_count(mfb_ctx* h) { return h ? h->c.launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+// K1 sgd_epoch, K5 sse_reduce, K8 philox_normal_fill   - hand-written sm_100a CUDA.
+//
+// sgd_epoch replaces SgdFilter::operator() (mf.h:76-132).  Per rating, with old values on the
+// right-hand side:
+//     e      = eta * (r - <theta_u, phi_v> - bu[u] - bv[v] - gb)
+//     theta' = lameta*theta + e*phi        phi' = lameta*phi + e*theta
+//     bu'    = lameta*bu + e               bv'  = lameta*bv + e         lameta = 1 - eta*lambda
+// Mapping: one group of LPR lanes owns a user-run (all records of one user inside one block of the
+// file, mf.h:83-88).  theta_u and bu[u] stay in registers for the whole run and are written once;
+// phi rows are gathered/scattered as coalesced 128-bit accesses that are served by the L2 when
+// the item matrix fits (Netflix shape: 9.1 MB of 126 MB).  Runs are pulled in file order from a
+// device-side queue, so execution is Hogwild over item rows exactly like the reference with
+// --fly N, only wider.  This path is gather/scatter bound (about 0.5 flop/B): no tensor cores.
+#include <algorithm>
+
+#include "mfb_group.cuh"
+#include "mfb_internal.h"
+#include "mfb_philox.cuh"
+
+namespace mfb {
+
+struct SgdArgs {
+  float* theta;
+  float* phi;
+  float* bu;
+  float* bv;
+  const int32_t* run_uid;
+  const int32_t* run_off;
+  const int32_t* vid;
+  const float* rating;
+  int* counter;
+  int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
+  float eta, lameta, lm1, gb;
+};
+
+// One rating, fast arithmetic (fused multiply-adds, butterfly dot).
+template <int LPR, int VPL, int MODE>
+__device__ __forceinline__ void sgd_update_fast(const SgdArgs& a, Row<VPL>& t, float& bu,
+                                                const Row<VPL>& f, float bvv, int v, float r,
+                                                int gl, unsigned m) {
+  const float d = group_dot<LPR, VPL>(t, f, m);
+  const float e = a.eta * (r - d - bu - bvv - a.gb);
+  Row<VPL> nf;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const float4 tt = t.v[i], ff = f.v[i];
+    if (MODE == MFB_MODE_ATOMIC) {  // increment of phi: (lameta-1)*phi + e*theta
+      nf.v[i] = make_float4(fmaf(e, tt.x, a.lm1 * ff.x), fmaf(e, tt.y, a.lm1 * ff.y),
+                            fmaf(e, tt.z, a.lm1 * ff.z), fmaf(e, tt.w, a.lm1 * ff.w));
+    } else {
+      nf.v[i] = make_float4(fmaf(e, tt.x, a.lameta * ff.x), fmaf(e, tt.y, a.lameta * ff.y),
+                            fmaf(e, tt.z, a.lameta * ff.z), fmaf(e, tt.w, a.lameta * ff.w));
+    }
+    t.v[i] = make_float4(fmaf(e, ff.x, a.lameta * tt.x), fmaf(e, ff.y, a.lameta * tt.y),
+                         fmaf(e, ff.z, a.lameta * tt.z), fmaf(e, ff.w, a.lameta * tt.w));
+  }
+  if (MODE == MFB_MODE_ATOMIC) {
+    red_add_row<LPR, VPL>(a.phi, v, a.nvec, gl, nf);
+    if (gl == 0) atomicAdd(a.bv + v, fmaf(a.lm1, bvv, e));
+  } else {
+    store_row<LPR, VPL>(a.phi, v, a.nvec, gl, nf);
+    if (gl == 0) __stcg(a.bv + v, fmaf(a.lameta, bvv, e));
+  }
+  bu = fmaf(a.lameta, bu, e);
+}
+
+// One rating in the oracle's operation order (mf.h:94-109 as restated in oracle/mf_oracle.c):
+// every multiply and add rounded separately, dot accumulated in coordinate order.
+template <int LPR, int VPL>
+__device__ __forceinline__ void sgd_update_exact(const SgdArgs& a, Row<VPL>& t, float& bu,
+                                                 const Row<VPL>& f, float bvv, int v, float r,
+                                                 int gl, unsigned m) {
+  const float d = group_dot_ordered<LPR, VPL>(t, f, gl, m);
+  float e = __fsub_rn(__fsub_rn(__fsub_rn(__fsub_rn(r, d), bu), bvv), a.gb);  // mf.h:99-101
+  e = __fmul_rn(a.eta, e);                                                     // mf.h:102
+  Row<VPL> nf;
+#define MFB_EXACT1(T, F)                                                                   \
+  {                                                                                        \
+    const float q = __fmul_rn(e, T);                          /* mf.h:103 q = e*theta   */ \
+    float th = __fadd_rn(T, __fmul_rn(a.lm1, T));             /* mf.h:104               */ \
+    th = __fadd_rn(th, __fmul_rn(e, F));                      /* mf.h:105               */ \
+    F = __fadd_rn(q, __fmul_rn(a.lameta, F));                 /* mf.h:106-107           */ \
+    T = th;                                                                                \
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    float4 tt = t.v[i], ff = f.v[i];
+    MFB_EXACT1(tt.x, ff.x) MFB_EXACT1(tt.y, ff.y) MFB_EXACT1(tt.z, ff.z) MFB_EXACT1(tt.w, ff.w)
+    t.v[i] = tt;
+    nf.v[i] = ff;
+  }
+#undef MFB_EXACT1
+  store_row<LPR, VPL>(a.phi, v, a.nvec, gl, nf);
+  if (gl == 0) __stcg(a.bv + v, __fadd_rn(__fmul_rn(a.lameta, bvv), e));  // mf.h:109
+  bu = __fadd_rn(__fmul_rn(a.lameta, bu), e);                             // mf.h:108
+}
+
+template <int LPR, int VPL, int MODE, int B>
+__global__ void __launch_bounds__(256) sgd_epoch_kernel(const SgdArgs a) {
+  constexpr bool ORDERED = (MODE == MFB_MODE_ORDERED);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const unsigned m = group_mask<LPR>();
+  if (ORDERED && (blockIdx.x != 0 || threadIdx.x >= LPR)) return;  // a single group walks the file
+  int next = a.run_begin;
+  for (;;) {
+    int run;
+    if (ORDERED) {
+      run = next++;
+    } else {
+      if (gl == 0) run = a.run_begin + atomicAdd(a.counter, 1);
+      run = __shfl_sync(m, run, 0, LPR);
+    }
+    if (run >= a.nruns) break;
+    const int uid = __ldg(a.run_uid + run);
+    const int lo = __ldg(a.run_off + run), hi = __ldg(a.run_off + run + 1);
+    if (lo == hi) continue;
+    Row<VPL> t = load_row<LPR, VPL>(a.theta, uid, a.nvec, gl);
+    float bu;
+    if (ORDERED) {  // the leader owns the scalar; other lanes must not read memory it wrote
+      bu = (gl == 0) ? __ldcg(a.bu + uid) : 0.f;
+      bu = __shfl_sync(m, bu, 0, LPR);
+    } else {
+      bu = __ldcg(a.bu + uid);
+    }
+    for (int j0 = lo; j0 < hi; j0 += LPR) {
+      const int nb = min(LPR, hi - j0);
+      int myvid = 0;
+      float myr = 0.f;
+      if (gl < nb) {  // one coalesced load of up to LPR records of the run
+        myvid = __ldcs(a.vid + j0 + gl);
+        myr = __ldcs(a.rating + j0 + gl);
+      }
+      for (int b0 = 0; b0 < nb; b0 += B) {
+        Row<VPL> f[B];
+        float bvv[B];
+        int v[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) {  // issue the B row gathers back to back
+          v[b] = __shfl_sync(m, myvid, (b0 + b) & (LPR - 1), LPR);
+          if (b0 + b < nb) {
+            f[b] = load_row<LPR, VPL>(a.phi, v[b], a.nvec, gl);
+            if (ORDERED) {
+              bvv[b] = (gl == 0) ? __ldcg(a.bv + v[b]) : 0.f;
+            } else {
+              bvv[b] = __ldcg(a.bv + v[b]);
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+          const float r = __shfl_sync(m, myr, (b0 + b) & (LPR - 1), LPR);
+          if (ORDERED) bvv[b] = __shfl_sync(m, bvv[b], 0, LPR);
+          if (b0 + b < nb) {
+            if (ORDERED)
+              sgd_update_exact<LPR, VPL>(a, t, bu, f[b], bvv[b], v[b], r, gl, m);
+            else
+              sgd_update_fast<LPR, VPL, MODE>(a, t, bu, f[b], bvv[b], v[b], r, gl, m);
+          }
+        }
+      }
+    }
+    store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
+    if (gl == 0) __stcg(a.bu + uid, bu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: MF::calc_mse (model.cc:41-73).  Same gather, read-only; fp32 error in the reference's
+// operation order, squared errors accumulated in fp64 (the reference accumulates per-block fp32
+// partials under a mutex in nondeterministic order; fp64 is the order-independent version).
+struct SseArgs {
+  const float* theta;
+  const float* phi;
+  const float* bu;
+  const float* bv;
+  const int32_t* run_uid;
+  const int32_t* run_off;
+  const int32_t* vid;
+  const float* rating;
+  double* accum;  // [0] += sum of squared errors
+  int nruns, nvec;
+  float gb;
+};
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) sse_kernel(const SseArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const unsigned m = group_mask<LPR>();
+  const int groups_per_cta = blockDim.x / LPR;
+  const int g = blockIdx.x * groups_per_cta + threadIdx.x / LPR;
+  const int G = gridDim.x * groups_per_cta;
+  double acc = 0.0;
+  for (int run = g; run < a.nruns; run += G) {
+    const int uid = __ldg(a.run_uid + run);
+    const int lo = __ldg(a.run_off + run), hi = __ldg(a.run_off + run + 1);
+    if (lo == hi) continue;
+    const Row<VPL> t = load_row<LPR, VPL>(a.theta, uid, a.nvec, gl);
+    const float bu = __ldcg(a.bu + uid);
+    for (int j0 = lo; j0 < hi; j0 += LPR) {
+      const int nb = min(LPR, hi - j0);
+      int myvid = 0;
+      float myr = 0.f;
+      if (gl < nb) {
+        myvid = __ldcs(a.vid + j0 + gl);
+        myr = __ldcs(a.rating + j0 + gl);
+      }
+      for (int b = 0; b < nb; b++) {
+        const int v = __shfl_sync(m, myvid, b, LPR);
+        const float r = __shfl_sync(m, myr, b, LPR);
+        const Row<VPL> f = load_row<LPR, VPL>(a.phi, v, a.nvec, gl);
+        const float d = group_dot<LPR, VPL>(t, f, m);
+        const float err = r - d - bu - __ldcg(a.bv + v) - a.gb;  // model.cc:62-63
+        if (gl == 0) acc += (double)(err * err);                 // model.cc:64
+      }
+    }
+  }
+  // block reduction: leaders hold partials
+  __shared__ double part[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += part[w];
+    atomicAdd(a.accum, s);
+  }
+}
+
+// K8: MF::init fill (model.cc:22-33): element = N(0,1)*scale, from Philox keyed by (array, index)
+__global__ void fill_normal_kernel(float* p, int64_t rows, int cols, int stride, uint64_t seed,
+                                   uint32_t which, float scale) {
+  const int cvec = (cols + 3) / 4;
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / cvec;
+    const int c4 = (int)(i - row * cvec);
+    const uint4 ctr = make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)c4, 0xF1110000u + which);
+    const float4 z = box_muller4(philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))));
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    for (int k = 0; k < 4; k++) {
+      const int c = c4 * 4 + k;
+      if (c < cols) p[row * stride + c] = zz[k] * scale;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+
+int pick_grid(Context* c, const void* kernel, int threads, int64_t groups_needed, int lpr) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  int64_t grid = (int64_t)c->sm_count * per_sm;  // persistent: a multiple of the SM count
+  const int groups_per_cta = threads / lpr;
+  const int64_t need = (groups_needed + groups_per_cta - 1) / groups_per_cta;
+  if (need < grid) grid = std::max<int64_t>(need, 1);
+  return (int)grid;
+}
+
+template <int LPR, int VPL>
+int launch_sgd_t(Context* c, const SgdArgs& a, int mode) {
+  const int threads = c->opt_threads;
+  dim3 grid, block(threads);
+  if (mode == MFB_MODE_ORDERED) {
+    sgd_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED, 1><<<1, 32, 0, c->stream>>>(a);
+  } else if (mode == MFB_MODE_ATOMIC) {
+    constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
+    auto k = sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>;
+    k<<<pick_grid(c, (const void*)k, threads, a.nruns - a.run_begin, LPR), threads, 0, c->stream>>>(a);
+  } else {
+    constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
+    auto k = sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
+    k<<<pick_grid(c, (const void*)k, threads, a.nruns - a.run_begin, LPR), threads, 0, c->stream>>>(a);
+  }
+  MFB_CUDA(cudaGetLastError());
+  c->launches++;
+  return MFB_OK;
+}
+
+template <int LPR, int VPL>
+int launch_sse_t(Context* c, const SseArgs& a) {
+  auto k = sse_kernel<LPR, VPL>;
+  k<<<pick_grid(c, (const void*)k, 256, a.nruns, LPR), 256, 0, c->stream>>>(a);
+  MFB_CUDA(cudaGetLastError());
+  c->launches++;
+  return MFB_OK;
+}
+
+}  // namespace
+
+// nvec = stride/4 float4 per row -> (lanes per row, vectors per lane)
+#define MFB_DISPATCH_SHAPE(nvec, CALL)                                    \
+  do {                                                                    \
+    if ((nvec) <= 4) { CALL(4, 1); }                                      \
+    else if ((nvec) <= 8) { CALL(8, 1); }                                 \
+    else if ((nvec) <= 16) { CALL(16, 1); }                               \
+    else if ((nvec) <= 32) { CALL(32, 1); }                               \
+    else if ((nvec) <= 64) { CALL(32, 2); }                               \
+    else if ((nvec) <= 128) { CALL(32, 4); }                              \
+    else if ((nvec) <= 256) { CALL(32, 8); }                              \
+    else if ((nvec) <= 512) { CALL(32, 16); }                             \
+    else { set_error("dim too large (max 2048)"); return MFB_E_ARG; }     \
+  } while (0)
+
+int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mode,
+               int64_t run_begin, int64_t run_end) {
+  SgdArgs a;
+  a.theta = c->arr[MFB_THETA];
+  a.phi = c->arr[MFB_PHI];
+  a.bu = c->arr[MFB_BU];
+  a.bv = c->arr[MFB_BV];
+  a.run_uid = d->d_run_uid;
+  a.run_off = d->d_run_off;
+  a.vid = d->d_vid;
+  a.rating = d->d_rating;
+  a.counter = c->d_counter;
+  a.run_begin = (int)run_begin;
+  a.nruns = (int)run_end;
+  a.nvec = c->stride / 4;
+  a.eta = eta;
+  a.lameta = (float)(1.0 - (double)(eta * lambda));  // mf.h:80
+  a.lm1 = (float)((double)a.lameta - 1.0);           // mf.h:104
+  a.gb = gb;
+  MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+#define CALL(L, V) return launch_sgd_t<L, V>(c, a, mode)
+  MFB_DISPATCH_SHAPE(a.nvec, CALL);
+#undef CALL
+  return MFB_OK;
+}
+
+int launch_sse(Context* c, Dataset* d, float gb) {
+  SseArgs a;
+  a.theta = c->arr[MFB_THETA];
+  a.phi = c->arr[MFB_PHI];
+  a.bu = c->arr[MFB_BU];
+  a.bv = c->arr[MFB_BV];
+  a.run_uid = d->d_run_uid;
+  a.run_off = d->d_run_off;
+  a.vid = d->d_vid;
+  a.rating = d->d_rating;
+  a.accum = c->d_accum;
+  a.nruns = (int)d->nruns;
+  a.nvec = c->stride / 4;
+  a.gb = gb;
+  MFB_CUDA(cudaMemsetAsync(c->d_accum, 0, sizeof(double), c->stream));
+#define CALL(L, V) return launch_sse_t<L, V>(c, a)
+  MFB_DISPATCH_SHAPE(a.nvec, CALL);
+#undef CALL
+  return MFB_OK;
+}
+
+int launch_fill_normal(Context* c, uint64_t seed, float scale) {
+  const int which[4] = {MFB_THETA, MFB_PHI, MFB_BU, MFB_BV};
+  for (int w = 0; w < 4; w++) {
+    const int64_t rows = array_rows(c, which[w]);
+    const int cols = array_cols(c, which[w]), stride = array_stride(c, which[w]);
+    if (rows == 0) continue;
+    // the bias vectors are filled as one row-major [rows][1] array
+    fill_normal_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->arr[which[w]], rows, cols, stride,
+                                                               seed, (uint32_t)which[w], scale);
+    MFB_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  return MFB_OK;
+}
+
+}  // namespace mfb

@@ -1,0 +1,183 @@
+/* mf_b200.h - C ABI of the B200 (sm_100a) implementation of experimental-mf's hot path:
+ * the blocked SGD matrix-factorization epoch (mf / dpmf / admf) and the test-RMSE pass.
+ *
+ * This is the drop-in boundary.  The reference has no FFI; its seam is the C++ object model
+ * (SURVEY.md 8b): tbb::pipeline calls `void* Filter::operator()(void* block)` on an mf::Block
+ * and the filter mutates the public arrays of an MF object.  Each entry point below names the
+ * reference interface it replaces (file:line under the reference's src/).  The host-side C++
+ * mirror of MF / DPMF / AdaptRegMF (experimental-mf_b200/csrc/model.h) is a thin wrapper over
+ * these calls; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative
+ * MFB_E_* code, with a thread-local message from mfb_last_error().  All factor math is fp32,
+ * ids are int32.  A context is bound to one CUDA device and one stream; calls on one context
+ * must come from one host thread at a time.  There is no CPU fallback: without a usable CUDA
+ * device mfb_create() fails with MFB_E_CUDA.
+ */
+#ifndef MF_B200_H
+#define MF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfb_ctx mfb_ctx;
+
+enum {
+  MFB_OK = 0,
+  MFB_E_ARG = -1,   /* bad argument / state */
+  MFB_E_CUDA = -2,  /* CUDA runtime error (message has the cudaError string) */
+  MFB_E_NOMEM = -3,
+  MFB_E_IO = -4,
+  MFB_E_COMM = -5   /* NCCL error */
+};
+
+/* model arrays (model.h:23 theta_/phi_/bu_/bv_; model.h:62 ur_/vr_/lambda_u_/lambda_v_;
+ * model.h:106 theta_old_/phi_old_/bu_old_/bv_old_) */
+enum {
+  MFB_THETA = 0, MFB_PHI = 1, MFB_BU = 2, MFB_BV = 3,
+  MFB_THETA_OLD = 4, MFB_PHI_OLD = 5, MFB_BU_OLD = 6, MFB_BV_OLD = 7,
+  MFB_UR = 8, MFB_VR = 9, MFB_LAMBDA_U = 10, MFB_LAMBDA_V = 11
+};
+
+/* update schedules */
+enum {
+  /* Hogwild: user-runs are handed to sub-warps in file order from a device-side queue; item
+   * rows are read and written without synchronisation (the reference with --fly N, mf.h:75). */
+  MFB_MODE_HOGWILD = 0,
+  /* Ordered: one sub-warp walks the file in file order - the reference's single-thread update
+   * order (--fly 1) - using the oracle's operation order (unfused mul/add, index-order dot), so
+   * results are bit-comparable with the CPU oracle.  A parity mode, not a fast one. */
+  MFB_MODE_ORDERED = 1,
+  /* Hogwild schedule, but item rows and item biases are updated with fp32 atomic adds
+   * (red.global.add.v4.f32) of the increment, so concurrent updates are never lost. */
+  MFB_MODE_ATOMIC = 2
+};
+
+const char* mfb_last_error(void);
+/* "x.y sm_100a"; also proves the library loads without a GPU */
+const char* mfb_version(void);
+/* row stride in floats used for a given dim: padding(dim), util.h:163-165 */
+int mfb_padding(int dim);
+
+/* ---- context: replaces MF::MF + MF::init storage (model.h:8-14, model.cc:10-21) ------------
+ * Allocates theta[nu][stride], phi[nv][stride], bu[nu], bv[nv] in HBM, zero-filled. */
+int mfb_create(mfb_ctx** out, int device, int nu, int nv, int dim);
+void mfb_destroy(mfb_ctx* ctx);
+/* run all work of this context on an existing cudaStream_t (e.g. torch's current stream) */
+int mfb_set_stream(mfb_ctx* ctx, void* cuda_stream);
+int mfb_sync(mfb_ctx* ctx);
+/* tuning knobs: "ctas_per_sm" (0 = occupancy maximum), "threads" (CTA size), "batch" */
+int mfb_set_option(mfb_ctx* ctx, const char* name, int value);
+/* allocate the optional array groups: 1 = admf shadows (*_OLD), 2 = dpmf (UR, VR, LAMBDA_*) */
+int mfb_enable(mfb_ctx* ctx, int group);
+
+/* ---- factor access: replaces direct theta_[i][j] access (model.h:23, model.cc:85-95) --------
+ * Copies rows [row0, row0+nrows) of a model array between a host matrix with `host_stride`
+ * floats per row (>= dim; pass 1 for the vector arrays) and the device. */
+int mfb_upload(mfb_ctx* ctx, int which, const float* host, int64_t row0, int64_t nrows,
+               int64_t host_stride);
+int mfb_download(mfb_ctx* ctx, int which, float* host, int64_t row0, int64_t nrows,
+                 int64_t host_stride);
+/* MF::init's fill (model.cc:22-33): every element ~ N(0,1)*scale from a Philox4x32-10 stream.
+ * (The reference uses a clock-seeded engine inside an OpenMP loop, i.e. it is unreproducible;
+ * parity tests upload explicit factors instead.) */
+int mfb_init_normal(mfb_ctx* ctx, uint64_t seed, float scale);
+/* admf init1 (model.cc:369-382): *_OLD <- current */
+int mfb_snapshot_old(mfb_ctx* ctx);
+/* raw device pointer of a model array (for NCCL / torch interop); NULL if not allocated */
+void* mfb_device_ptr(mfb_ctx* ctx, int which);
+
+/* ---- datasets: replace ParseFilter / plain_read (mf.h:57-69, util.h:76-88) ------------------
+ * A dataset is a rating file kept in file order as SoA tiles in HBM.  Blocks are appended as
+ * flat arrays: users of the block in order (uid[nusers]), rec_off[nusers+1] offsets into
+ * vid[]/rating[] relative to the block.  finalize() uploads and builds the schedules. */
+int mfb_dataset_create(mfb_ctx* ctx, int* ds);
+int mfb_dataset_append_block(mfb_ctx* ctx, int ds, int32_t nusers, const int32_t* uid,
+                             const int32_t* rec_off, const int32_t* vid, const float* rating);
+/* parse a whole [u32 size][mf.Block] file (getdata.cc:100-103) with the built-in wire decoder */
+int mfb_dataset_load_file(mfb_ctx* ctx, int ds, const char* path);
+int mfb_dataset_finalize(mfb_ctx* ctx, int ds);
+int mfb_dataset_free(mfb_ctx* ctx, int ds);
+int64_t mfb_dataset_num_ratings(mfb_ctx* ctx, int ds);
+int64_t mfb_dataset_num_runs(mfb_ctx* ctx, int ds);
+
+/* ---- host-side rating files (no GPU needed): replace plain_read (util.h:76-88) and the
+ * getdata writer (getdata.cc:82-126).  An mfb_blocks is a parsed [u32 size][mf.Block] file in file
+ * order as flat arrays: block_off[nblocks+1] (first run of each block), run_uid[nruns],
+ * run_off[nruns+1] (first record of each run), vid[n], rating[n]. */
+typedef struct mfb_blocks mfb_blocks;
+int mfb_blocks_read(const char* path, mfb_blocks** out);
+int mfb_blocks_from_arrays(int64_t nblocks, const int64_t* block_off, int64_t nruns,
+                           const int32_t* run_uid, const int32_t* run_off, const int32_t* vid,
+                           const float* rating, mfb_blocks** out);
+int mfb_blocks_write(const mfb_blocks* b, const char* path);
+void mfb_blocks_free(mfb_blocks* b);
+int64_t mfb_blocks_num_blocks(const mfb_blocks* b);
+int64_t mfb_blocks_num_runs(const mfb_blocks* b);
+int64_t mfb_blocks_num_ratings(const mfb_blocks* b);
+const int64_t* mfb_blocks_block_off(const mfb_blocks* b);
+const int32_t* mfb_blocks_run_uid(const mfb_blocks* b);
+const int32_t* mfb_blocks_run_off(const mfb_blocks* b);
+const int32_t* mfb_blocks_vid(const mfb_blocks* b);
+const float* mfb_blocks_rating(const mfb_blocks* b);
+/* append every block of a parsed file to a dataset (before finalize) */
+int mfb_dataset_append_blocks(mfb_ctx* ctx, int ds, const mfb_blocks* b);
+
+/* ---- synthetic ratings of a named shape (the reference ships no data).
+ * Counter-based (Philox4x32-10), so the result depends only on the parameters - not on the
+ * thread count, and a user range [user_begin, user_end) yields exactly that slice of the full
+ * data set (used to shard users over GPUs).  Planted rank-`rank` model U*,V* ~ N(0,1/4),
+ * r = clamp(round(gb + <u*,v*> + N(0, noise_sd^2)), 1, 5); user degree ~ lognormal(sigma) scaled
+ * to nnz; item popularity ~ Zipf(zipf_s) over a random item permutation; no duplicate (u,i).
+ * Layout mirrors getdata.cc --method userwise --split S + --method protobuf --size B
+ * (getdata.cc:21-126): train records are dealt into `split` chunks, each chunk grouped by user
+ * in a random user order, `users_per_block` users per Block.  test/valid are single chunks. */
+typedef struct {
+  int32_t nu, nv;
+  int64_t nnz;             /* total ratings (train + test + valid), approximate */
+  int32_t rank;            /* 16 */
+  float gb, noise_sd;      /* 2.76, 0.5 */
+  float degree_sigma;      /* 1.0 */
+  float zipf_s;            /* 1.0 */
+  float test_frac, valid_frac;
+  int32_t split;           /* 4 */
+  int32_t users_per_block; /* 500 */
+  uint64_t seed;           /* 0x4D46B200 */
+  int32_t user_begin, user_end; /* 0, nu for everything */
+  int32_t threads;         /* 0 = hardware concurrency */
+} mfb_gen_params;
+void mfb_gen_defaults(mfb_gen_params* p, int32_t nu, int32_t nv, int64_t nnz);
+int mfb_generate(const mfb_gen_params* p, mfb_blocks** train, mfb_blocks** test,
+                 mfb_blocks** valid);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * SgdFilter::operator() over every block of the file (mf.h:76-132): one SGD epoch with
+ * learning rate eta, regulariser lambda, global bias gb. */
+int mfb_sgd_epoch(mfb_ctx* ctx, int ds, float eta, float lambda, float gb, int mode);
+/* The same epoch with the rating tiles starting in HOST memory (the reference re-reads its
+ * training file every epoch, mf.h:24-45): the arrays of `src` (pin them once with
+ * mfb_blocks_pin) are copied H2D in chunks of about `chunk_ratings` records (0 = default) on a
+ * second stream, overlapped with the update kernel of the previous chunk.  `ds` must be a
+ * finalized dataset created from the same blocks; its HBM tiles are the copy target. */
+int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float eta, float lambda,
+                            float gb, int mode, int64_t chunk_ratings);
+int mfb_blocks_pin(mfb_blocks* b);
+int mfb_blocks_unpin(mfb_blocks* b);
+/* MF::calc_mse (model.cc:41-73): SUM of squared errors and the record count. */
+int mfb_sse(mfb_ctx* ctx, int ds, float gb, double* sse, int64_t* n);
+/* MF::seteta (model.cc:36-38) / DPMF::seteta_cutoff (model.cc:350-352): same formula, host side */
+float mfb_seteta(float eta0, int round, float gam);
+float mfb_seteta_cutoff(float eta0, int round, float gam, float mineta);
+
+/* device time in ms of the most recent epoch / sse call's kernels (CUDA events on the
+ * context's stream; valid after mfb_sync) and the number of kernel launches since create */
+float mfb_last_kernel_ms(mfb_ctx* ctx);
+int64_t mfb_launch_count(mfb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

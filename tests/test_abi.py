@@ -1,0 +1,145 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/mf_b200.h
+declares, and its host-only entry points (wire codec, generator, eta schedule) agree with the
+oracle.  No compute call is made here (no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mfb200 as mb
+import oraclelib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "mf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = mb.lib()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(L, s), "libmf_b200.so does not export %s" % s
+        assert s in mb.SIGNATURES, "python binding lacks %s" % s
+    assert sorted(mb.SIGNATURES) == syms  # and the binding names nothing the header lacks
+    assert b"sm_100a" in L.mfb_version()
+
+
+def test_library_contains_sm100a_code_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", mb.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_padding_and_eta_match_oracle(oracle_lib):
+    L = mb.lib()
+    for d in (1, 15, 16, 17, 20, 32, 64, 100, 128, 2048):
+        assert L.mfb_padding(d) == oracle_lib.mfo_padding(d)
+    for eta0, rnd, gam in ((2e-2, 1, 1.0), (2e-2, 9, 1.0), (4e-2, 5, 0.6), (2e-10, 3, 0.3)):
+        assert np.float32(L.mfb_seteta(eta0, rnd, gam)) == np.float32(oracle_lib.mfo_seteta(eta0, rnd, gam))
+        assert np.float32(L.mfb_seteta_cutoff(eta0, rnd, gam, 1e-9)) == \
+            np.float32(oracle_lib.mfo_seteta_cutoff(eta0, rnd, gam, 1e-9))
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA device the product refuses to run (MFB_E_CUDA + message)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = mb.lib().mfb_create(C.byref(h), 0, 10, 10, 8)
+    assert rc == -2 and not h.value
+    assert b"cuda" in mb.lib().mfb_last_error().lower()
+    with pytest.raises(mb.MfbError):
+        mb.Context(10, 10, 8)
+
+
+def test_wire_decoder_on_reference_parsed_bytes(golden, tmp_path):
+    p = tmp_path / "train.bin"
+    golden["train_bytes"].tofile(p)
+    b = mb.Blocks.read(str(p))
+    for name in ("block_off", "run_uid", "run_off", "vid", "rating"):
+        np.testing.assert_array_equal(getattr(b, name), golden["train_" + name])
+    q = tmp_path / "again.bin"
+    b.write(str(q))
+    assert q.read_bytes() == p.read_bytes()
+
+
+def test_wire_kat_and_errors(tmp_path):
+    frame = bytes.fromhex("170000000a1508ac021207080b150000a04012070815150000" "4040")
+    p = tmp_path / "kat.bin"
+    p.write_bytes(frame)
+    b = mb.Blocks.read(str(p))
+    assert (b.nblocks, b.run_uid.tolist(), b.vid.tolist(), b.rating.tolist()) == (1, [300], [11, 21], [5.0, 3.0])
+    # empty file, empty block, truncated frame, missing file
+    (tmp_path / "empty.bin").write_bytes(b"")
+    assert mb.Blocks.read(str(tmp_path / "empty.bin")).nblocks == 0
+    (tmp_path / "emptyblock.bin").write_bytes(b"\x00\x00\x00\x00")
+    e = mb.Blocks.read(str(tmp_path / "emptyblock.bin"))
+    assert (e.nblocks, e.nruns, e.nratings) == (1, 0, 0)
+    (tmp_path / "trunc.bin").write_bytes(frame[:-3])
+    with pytest.raises(mb.MfbError):
+        mb.Blocks.read(str(tmp_path / "trunc.bin"))
+    with pytest.raises(mb.MfbError):
+        mb.Blocks.read(str(tmp_path / "nope.bin"))
+
+
+def test_wire_roundtrip_agrees_with_oracle_codec(oracle_lib, tmp_path):
+    train, test, _ = ol.make_ratings(200, 90, 5000, seed=12)
+    p = train.write(str(tmp_path / "o.bin"))  # written by the oracle's encoder
+    b = mb.Blocks.read(p)
+    np.testing.assert_array_equal(b.vid, train.vid)
+    np.testing.assert_array_equal(b.run_off, train.run_off)
+    np.testing.assert_array_equal(b.block_off, train.block_off)
+    q = mb.Blocks.from_arrays(train.block_off, train.run_uid, train.run_off, train.vid, train.rating).write(
+        str(tmp_path / "p.bin"))
+    assert open(p, "rb").read() == open(q, "rb").read()
+    d = ol.Dataset.read(q)  # and the oracle reads what the product wrote
+    np.testing.assert_array_equal(d.rating, train.rating)
+
+
+def test_generator_shape_determinism_and_sharding():
+    nu, nv, nnz = 3000, 700, 120000
+    p = mb.gen_params(nu, nv, nnz, test_frac=0.1, valid_frac=0.05, users_per_block=100)
+    tr, te, va = mb.generate(p)
+    total = tr.nratings + te.nratings + va.nratings
+    assert abs(total - nnz) < 0.03 * nnz
+    assert abs(te.nratings / total - 0.1) < 0.01 and abs(va.nratings / total - 0.05) < 0.01
+    assert set(np.unique(tr.rating)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+    assert tr.vid.min() >= 0 and tr.vid.max() < nv and tr.run_uid.max() < nu
+    # no duplicate (u,i) across train+test+valid
+    keys = []
+    for b in (tr, te, va):
+        u = np.repeat(b.run_uid, np.diff(b.run_off)).astype(np.int64)
+        keys.append(u * nv + b.vid)
+    keys = np.concatenate(keys)
+    assert len(np.unique(keys)) == len(keys)
+    # getdata-style layout: 4 chunks, each user at most once per chunk, blocks of <= 100 users
+    assert np.diff(tr.block_off).max() <= 100
+    counts = np.bincount(tr.run_uid, minlength=nu)
+    assert counts.max() <= 4
+    # popularity is skewed, degrees are skewed
+    pop = np.sort(np.bincount(tr.vid, minlength=nv))[::-1]
+    assert pop[:nv // 10].sum() > 0.3 * tr.nratings
+    # same data for any thread count; a user range reproduces exactly that slice
+    p1 = mb.gen_params(nu, nv, nnz, test_frac=0.1, valid_frac=0.05, users_per_block=100, threads=1)
+    tr1, _, _ = mb.generate(p1)
+    np.testing.assert_array_equal(tr1.vid, tr.vid)
+    np.testing.assert_array_equal(tr1.rating, tr.rating)
+    ps = mb.gen_params(nu, nv, nnz, test_frac=0.1, valid_frac=0.05, users_per_block=100,
+                       user_begin=500, user_end=1700)
+    trs, _, _ = mb.generate(ps)
+    u_all = np.repeat(tr.run_uid, np.diff(tr.run_off))
+    m = (u_all >= 500) & (u_all < 1700)
+    np.testing.assert_array_equal(np.repeat(trs.run_uid, np.diff(trs.run_off)), u_all[m])
+    np.testing.assert_array_equal(trs.vid, tr.vid[m])
+    np.testing.assert_array_equal(trs.rating, tr.rating[m])

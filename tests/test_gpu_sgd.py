@@ -1,0 +1,185 @@
+"""Parity of the CUDA SGD epoch and evaluation pass (through the C ABI) with the CPU oracle.
+
+Tolerances (north star): ordered mode per row <= 1e-5 relative - in fact the ordered kernel uses
+the oracle's operation order and is expected to be BIT-EXACT; Hogwild final test RMSE within 1e-3
+absolute of the serial oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mfb200 as mb
+import oraclelib as ol
+from gpu_common import (ctx_from_model, model_equal, model_rel_err, oracle_sgd, oracle_sse,
+                        row_rel_err, upload_ds)
+from test_oracle_golden import init_model, load_ds
+
+pytestmark = pytest.mark.gpu
+GB = 2.76
+
+
+def test_ordered_sgd_reproduces_reference_golden_bit_exact(golden):
+    """CUDA ordered mode vs outputs of the reference's own SgdFilter (tests/golden)."""
+    g = golden
+    m, train, test = init_model(g), load_ds(g, "train"), load_ds(g, "test")
+    eta0, gam, lam = [float(x) for x in g["sgd_params"]]
+    gb = float(g["gb"])
+    c = ctx_from_model(m)
+    tr, te = upload_ds(c, train), upload_ds(c, test)
+    for ep in (1, 2, 3):
+        eta = mb.seteta(eta0, ep, gam)
+        assert np.float32(eta) == g["sgd_eta_%d" % ep]
+        c.sgd_epoch(tr, eta, lam, gb, mb.MODE_ORDERED)
+        th, ph, bu, bv = c.get_factors()
+        np.testing.assert_array_equal(th, g["sgd_theta_%d" % ep])
+        np.testing.assert_array_equal(ph, g["sgd_phi_%d" % ep])
+        np.testing.assert_array_equal(bu, g["sgd_bu_%d" % ep])
+        np.testing.assert_array_equal(bv, g["sgd_bv_%d" % ep])
+        s, n = c.sse(te, gb)
+        assert n == int(g["sgd_test_n_%d" % ep])
+        assert abs(s - float(g["sgd_test_sse_%d" % ep])) <= 2e-6 * s
+    c.close()
+
+
+@pytest.mark.parametrize("dim", [8, 16, 20, 32, 50, 64, 100, 128, 200, 256, 500])
+def test_ordered_sgd_matches_oracle_all_row_shapes(dim):
+    """every (lanes-per-row, vectors-per-lane) instantiation, incl. rows with padding columns"""
+    nu, nv = 150, 90
+    train, test, _ = ol.make_ratings(nu, nv, 4000, seed=dim)
+    m = ol.Model(nu, nv, dim, seed=dim + 1, scale=0.1)
+    c = ctx_from_model(m)
+    tr, te = upload_ds(c, train), upload_ds(c, test)
+    for ep in (1, 2):
+        eta = mb.seteta(3e-2, ep, 1.0)
+        c.sgd_epoch(tr, eta, 1e-2, GB, mb.MODE_ORDERED)
+        oracle_sgd(m, train, eta, 1e-2, GB)
+        assert model_rel_err(c, m) <= 1e-5
+        assert model_equal(c, m), "ordered mode is expected to be bit-exact"
+    s, n = c.sse(te, GB)
+    so, no = oracle_sse(m, test, GB)
+    assert n == no and abs(s - so) <= 1e-5 * so
+    c.close()
+
+
+@pytest.mark.parametrize("mode", [mb.MODE_HOGWILD, mb.MODE_ATOMIC])
+@pytest.mark.parametrize("dim", [16, 32, 64, 128, 256])
+def test_parallel_modes_exact_on_conflict_free_data(mode, dim):
+    """Size-independent property: when no two ratings share a user or an item the update order
+    cannot matter, so the parallel schedules must agree with the serial oracle (up to the
+    fused-multiply-add / butterfly-sum rounding of the fast path)."""
+    n = 20000
+    rng = np.random.default_rng(dim)
+    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1),
+                    rng.permutation(n), rng.integers(1, 6, n))
+    m = ol.Model(n, n, dim, seed=3, scale=0.3)
+    c = ctx_from_model(m)
+    d = upload_ds(c, ds)
+    c.sgd_epoch(d, 0.05, 0.02, GB, mode)
+    oracle_sgd(m, ds, 0.05, 0.02, GB)
+    assert model_rel_err(c, m) <= 5e-6
+    c.close()
+
+
+def test_edge_cases_empty_and_ragged_runs():
+    nu, nv, dim = 40, 70, 32
+    m = ol.Model(nu, nv, dim, seed=1, scale=0.2)
+    c = ctx_from_model(m)
+    # empty data set
+    e = c.dataset_from_arrays([0], [], [0], [], [])
+    c.sgd_epoch(e, 0.1, 0.1, GB, mb.MODE_HOGWILD)
+    c.sgd_epoch(e, 0.1, 0.1, GB, mb.MODE_ORDERED)
+    assert c.sse(e, GB) == (0.0, 0)
+    assert model_equal(c, m)
+    # users without records, an empty block, run lengths around the lane-batch size, one record
+    rng = np.random.default_rng(0)
+    lens = [0, 1, 7, 8, 9, 31, 32, 33, 0, 64, 65, 3]
+    run_off = np.r_[0, np.cumsum(lens)]
+    vids = np.concatenate([rng.permutation(nv)[:l] for l in lens]).astype(np.int32)
+    ds = ol.Dataset([0, 3, 3, 8, 12], np.arange(len(lens)), run_off, vids,
+                    rng.integers(1, 6, run_off[-1]))
+    d = upload_ds(c, ds)
+    assert c.num_ratings(d) == run_off[-1] and c.num_runs(d) == len(lens)
+    c.sgd_epoch(d, 0.05, 0.02, GB, mb.MODE_ORDERED)
+    oracle_sgd(m, ds, 0.05, 0.02, GB)
+    assert model_equal(c, m)
+    s, n = c.sse(d, GB)
+    so, no = oracle_sse(m, ds, GB)
+    assert n == no and abs(s - so) <= 1e-5 * so
+    # eta = 0 leaves the model untouched (idempotence), in every mode
+    for mode in (mb.MODE_HOGWILD, mb.MODE_ATOMIC, mb.MODE_ORDERED):
+        c.sgd_epoch(d, 0.0, 0.02, GB, mode)
+    assert model_rel_err(c, m) <= 1e-7
+    c.close()
+
+
+def test_argument_errors_are_reported():
+    c = mb.Context(10, 10, 8)
+    with pytest.raises(mb.MfbError):
+        c.sgd_epoch(99, 0.1, 0.1, GB)  # unknown data set
+    with pytest.raises(mb.MfbError):
+        c.dataset_from_arrays([0, 1], [10], [0, 1], [0], [1.0])  # uid out of range
+    with pytest.raises(mb.MfbError):
+        c.dataset_from_arrays([0, 1], [0], [0, 1], [10], [1.0])  # vid out of range
+    with pytest.raises(mb.MfbError):
+        mb.Context(10, 10, 4096)
+    c.close()
+
+
+def test_file_ingest_equals_array_ingest(tmp_path):
+    nu, nv, dim = 300, 120, 64
+    train, _, _ = ol.make_ratings(nu, nv, 9000, seed=7)
+    path = train.write(str(tmp_path / "train.bin"))
+    m = ol.Model(nu, nv, dim, seed=2)
+    c1, c2 = ctx_from_model(m), ctx_from_model(m)
+    d1 = c1.dataset_from_file(path)
+    d2 = upload_ds(c2, train)
+    assert c1.num_ratings(d1) == c2.num_ratings(d2) == train.nratings
+    c1.sgd_epoch(d1, 0.02, 5e-3, GB, mb.MODE_ORDERED)
+    c2.sgd_epoch(d2, 0.02, 5e-3, GB, mb.MODE_ORDERED)
+    for a, b in zip(c1.get_factors(), c2.get_factors()):
+        np.testing.assert_array_equal(a, b)
+    c1.close()
+    c2.close()
+
+
+def test_hogwild_rmse_matches_serial_oracle_ml1m_shape():
+    """configs[0]: MovieLens-1M-shaped, k=32, 10 epochs; |tRMSE_gpu - tRMSE_oracle| <= 1e-3."""
+    nu, nv, dim, epochs = 6040, 3706, 32, 10
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, 1_000_000, test_frac=0.1))
+    train = ol.Dataset(tr.block_off, tr.run_uid, tr.run_off, tr.vid, tr.rating)
+    test = ol.Dataset(te.block_off, te.run_uid, te.run_off, te.vid, te.rating)
+    m = ol.Model(nu, nv, dim, seed=11)
+    out = {}
+    for mode in (mb.MODE_HOGWILD, mb.MODE_ATOMIC):
+        c = ctx_from_model(m)
+        dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+        out[mode] = []
+        for ep in range(1, epochs + 1):
+            c.sgd_epoch(dtr, mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mode)
+            out[mode].append(c.rmse(dte, GB))
+        c.close()
+    want = []
+    for ep in range(1, epochs + 1):
+        oracle_sgd(m, train, mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
+        s, n = oracle_sse(m, test, GB)
+        want.append(float(np.sqrt(s / n)))
+    print("oracle ", ["%.5f" % x for x in want])
+    print("hogwild", ["%.5f" % x for x in out[mb.MODE_HOGWILD]])
+    print("atomic ", ["%.5f" % x for x in out[mb.MODE_ATOMIC]])
+    assert want[-1] < want[0]  # it learns
+    assert abs(out[mb.MODE_HOGWILD][-1] - want[-1]) <= 1e-3
+    assert abs(out[mb.MODE_ATOMIC][-1] - want[-1]) <= 1e-3
+
+
+def test_init_normal_statistics():
+    c = mb.Context(5000, 3000, 64)
+    c.init_normal(123, 1e-2)
+    th, ph, bu, bv = c.get_factors()
+    for a in (th, ph, bu, bv):
+        a = a.astype(np.float64)
+        assert abs(a.mean()) < 5e-4 and abs(a.std() - 1e-2) < 3e-4
+    c2 = mb.Context(5000, 3000, 64)
+    c2.init_normal(123, 1e-2)
+    np.testing.assert_array_equal(c2.download(mb.THETA), th)  # counter-based: reproducible
+    c.close()
+    c2.close()
