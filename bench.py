@@ -186,7 +186,8 @@ def workload_config(wl, n_gpus):
     nu, nv, nnz, k, _ = WORKLOADS[wl]
     return {"workload": "%s-shaped synthetic (%d users x %d items, %d ratings) SGD MF k=%d fp32" % (wl, nu, nv, nnz, k),
             "nu": nu, "nv": nv, "ratings": nnz, "k": k, "alg": "mf", "eta": ETA0, "lambda": LAMBDA,
-            "schedule": "hogwild", "parallelism": "1 GPU" if n_gpus == 1 else "dsgd%d" % n_gpus,
+            "schedule": "parallel user-runs, atomic (red.add.v4.f32) item-row accumulation, bounded concurrency",
+            "parallelism": "1 GPU" if n_gpus == 1 else "dsgd%d" % n_gpus,
             "l2": "inputs larger than L2: each epoch streams the rating tiles (8 B/rating) and all user rows"}
 
 
@@ -301,7 +302,7 @@ def run_b200_arm(args, wl):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "sgd_epoch_kernel<32,1,hogwild>" if k == 128 else "sgd_epoch_kernel",
+                     "kernel": "sgd_epoch_kernel<LPR=32,VPL=1,%s>" % args.schedule if k == 128 else "sgd_epoch_kernel",
                      "kernel_ms": kavg, "bytes_per_update": bytes_per_update(k), "updates_per_launch": ntrain,
                      "note": "algorithmic bytes; theta rows stay in registers across a user-run and phi rows are "
                              "served by L2, so DRAM traffic is far lower (see profiles/)"},
@@ -324,7 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
-    ap.add_argument("--schedule", default="hogwild", choices=["hogwild", "atomic"])
+    ap.add_argument("--schedule", default="atomic", choices=["hogwild", "atomic"])
     ap.add_argument("--chunk", type=int, default=0, help="ratings per H2D chunk in the e2e leg")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="ratings in the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")

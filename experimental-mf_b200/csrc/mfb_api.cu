@@ -50,6 +50,40 @@ static int alloc_array(Context* c, int which) {
   return MFB_OK;
 }
 
+LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
+                        double max_item_share, int64_t total_runs) {
+  int max_threads = c->opt_threads;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, max_threads, 0);
+  per_sm = std::max(per_sm, 1);
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  const int groups_per_warp = 32 / lpr;
+  int64_t groups = (int64_t)c->sm_count * per_sm * (max_threads / 32) * groups_per_warp;  // hardware
+  groups = std::min(groups, std::max<int64_t>(groups_needed, 1));
+  if (c->opt_max_groups > 0) {
+    groups = std::min<int64_t>(groups, c->opt_max_groups);
+  } else {
+    if (c->opt_row_concurrency > 0 && max_item_share > 0.0)
+      groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(c->opt_row_concurrency / max_item_share)));
+    if (c->opt_run_fraction_ppm > 0 && total_runs > 0)
+      groups = std::min<int64_t>(groups, std::max<int64_t>(1, total_runs * c->opt_run_fraction_ppm / 1000000));
+  }
+  // spread the warps over all SMs: one CTA per SM with as many warps as needed, more CTAs beyond 8
+  const int64_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
+  LaunchShape ls;
+  if (warps <= c->sm_count) {
+    ls.grid = (int)warps;
+    ls.threads = 32;
+  } else {
+    const int warps_per_sm = (int)((warps + c->sm_count - 1) / c->sm_count);
+    const int max_wpc = max_threads / 32;
+    const int ctas = (warps_per_sm + max_wpc - 1) / max_wpc;
+    ls.threads = 32 * ((warps_per_sm + ctas - 1) / ctas);
+    ls.grid = c->sm_count * ctas;
+  }
+  return ls;
+}
+
 static Dataset* get_ds(Context* c, int ds) {
   if (ds < 0 || ds >= (int)c->datasets.size() || !c->datasets[ds].used) {
     set_error("bad dataset id %d", ds);
@@ -168,6 +202,8 @@ void mfb_destroy(mfb_ctx* h) {
   for (auto& p : c->arr) cudaFree(p);
   cudaFree(c->d_counter);
   cudaFree(c->d_accum);
+  cudaFree(c->d_noise_table);
+  cudaFree(c->d_norms);
   cudaFreeHost(c->h_accum);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -202,6 +238,17 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "threads")) {
     MFB_REQUIRE(value == 32 || value == 64 || value == 128 || value == 256, "threads must be 32/64/128/256");
     c->opt_threads = value;
+  } else if (!strcmp(name, "row_concurrency")) {
+    MFB_REQUIRE(value >= 0, "row_concurrency must be >= 0");
+    c->opt_row_concurrency = value;
+  } else if (!strcmp(name, "run_fraction_ppm")) {
+    MFB_REQUIRE(value >= 0, "run_fraction_ppm must be >= 0");
+    c->opt_run_fraction_ppm = value;
+  } else if (!strcmp(name, "max_groups")) {
+    MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
+    c->opt_max_groups = value;
+  } else if (!strcmp(name, "memopt")) {
+    c->opt_memopt = value;
   } else {
     set_error("unknown option %s", name);
     return MFB_E_ARG;
@@ -370,6 +417,36 @@ int mfb_dataset_finalize(mfb_ctx* h, int ds) {
   if ((rc = to_device(c, d->h_run_off, &d->d_run_off))) return rc;
   if ((rc = to_device(c, d->h_vid, &d->d_vid))) return rc;
   if ((rc = to_device(c, d->h_rating, &d->d_rating))) return rc;
+  {
+    std::vector<int32_t> cnt(c->nv, 0);
+    int32_t top = 0;
+    for (int32_t v : d->h_vid) top = std::max(top, ++cnt[v]);
+    d->max_item_share = d->nratings ? (double)top / (double)d->nratings : 0.0;
+  }
+  if (c->arr[MFB_UR]) {  // dpmf enabled: static logical clock + per-row record counts
+    std::vector<int32_t> last_u(c->nu, 0), last_v(c->nv, 0), run_uc(d->nruns, 0), vc(d->nratings, 0);
+    d->h_ucount.assign(c->nu, 0);
+    d->h_vcount.assign(c->nv, 0);
+    for (int64_t r = 0; r < d->nruns; r++) {
+      const int32_t u = d->h_run_uid[r];
+      const int32_t lo = d->h_run_off[r], hi = d->h_run_off[r + 1];
+      if (lo == hi) continue;
+      run_uc[r] = lo - last_u[u];          // dpmf.h:65: uc = gc - gcountu[uid], gc == record index
+      last_u[u] = hi - 1;                  // dpmf.h:66
+      d->h_ucount[u] += hi - lo;
+      for (int32_t t = lo; t < hi; t++) {
+        const int32_t v = d->h_vid[t];
+        vc[t] = t - last_v[v];             // dpmf.h:63
+        last_v[v] = t;
+        d->h_vcount[v]++;
+      }
+    }
+    if ((rc = to_device(c, run_uc, &d->d_uc))) return rc;
+    if ((rc = to_device(c, vc, &d->d_vc))) return rc;
+    if ((rc = to_device(c, last_u, &d->d_last_u))) return rc;
+    if ((rc = to_device(c, last_v, &d->d_last_v))) return rc;
+    MFB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above die at the end of this scope
+  }
   MFB_CUDA(cudaStreamSynchronize(c->stream));
   // the tiles are resident in HBM; drop the host staging copies (keep the small run tables)
   release(d->h_vid);
@@ -519,6 +596,111 @@ int mfb_sse(mfb_ctx* h, int ds, float gb, double* sse, int64_t* n) {
   MFB_CUDA(cudaMemcpyAsync(c->h_accum, c->d_accum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   MFB_CUDA(cudaStreamSynchronize(c->stream));
   *sse = c->h_accum[0];
+  return MFB_OK;
+}
+
+// ---- dpmf ------------------------------------------------------------------------------------
+float mfb_dp_bound(float epsilon, int tau, int nv) {  // model.cc:239-242
+  if (tau <= 0) tau = nv;
+  if (epsilon <= 0.0f) return 1.0f;
+  return (float)((double)epsilon * 1.0 / (4.0 * 25.0 * (double)tau));
+}
+
+int mfb_dp_weights(mfb_ctx* h, int ds, int32_t* ntrain) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(d->finalized && d->d_vc, "dataset %d was not finalized with dpmf enabled", ds);
+  MFB_CUDA(cudaSetDevice(c->device));
+  const int32_t n = (int32_t)d->nratings;
+  std::vector<float> ur(c->nu), vr(c->nv);
+  for (int i = 0; i < c->nu; i++) ur[i] = (float)n / d->h_ucount[i];  // model.cc:294 (inf if unseen)
+  for (int i = 0; i < c->nv; i++) vr[i] = (float)n / d->h_vcount[i];  // model.cc:295
+  MFB_CUDA(cudaMemcpyAsync(c->arr[MFB_UR], ur.data(), ur.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  MFB_CUDA(cudaMemcpyAsync(c->arr[MFB_VR], vr.data(), vr.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  if (ntrain) *ntrain = n;
+  return MFB_OK;
+}
+
+static int check_sgld(Context* c, Dataset* d, const mfb_sgld_params* p) {
+  MFB_REQUIRE(p, "params are NULL");
+  MFB_REQUIRE(c->arr[MFB_UR] && c->arr[MFB_LAMBDA_U], "dpmf arrays not enabled (mfb_enable(ctx, 2))");
+  MFB_REQUIRE(d->finalized && d->d_vc, "dataset was not finalized with dpmf enabled");
+  MFB_REQUIRE(!p->use_table || c->d_noise_table, "no noise table uploaded");
+  return MFB_OK;
+}
+
+int mfb_sgld_epoch(mfb_ctx* h, int ds, const mfb_sgld_params* p, float gb, int mode) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  int rc = check_sgld(c, d, p);
+  if (rc) return rc;
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED, "bad mode %d", mode);
+  MFB_REQUIRE(!p->use_table || mode == MFB_MODE_ORDERED, "table noise is an ordered-mode (parity) feature");
+  if (p->use_table) {
+    int64_t longest = 0;
+    for (int64_t r = 0; r < d->nruns; r++) longest = std::max<int64_t>(longest, d->h_run_off[r + 1] - d->h_run_off[r]);
+    MFB_REQUIRE(p->table_offset >= 0 && p->table_offset + longest * (c->dim + 1) <= c->noise_table_size,
+                "noise table too small for offset %d", p->table_offset);
+  }
+  MFB_CUDA(cudaSetDevice(c->device));
+  begin_timing(c);
+  rc = d->nruns ? launch_sgld(c, d, p, gb, mode) : MFB_OK;
+  end_timing(c);
+  return rc;
+}
+
+int mfb_sgld_flush_noise(mfb_ctx* h, int ds, const mfb_sgld_params* p) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  int rc = check_sgld(c, d, p);
+  if (rc) return rc;
+  MFB_REQUIRE(!p->use_table || p->table_offset + c->dim + 1 <= c->noise_table_size, "noise table too small");
+  MFB_CUDA(cudaSetDevice(c->device));
+  begin_timing(c);
+  rc = launch_flush(c, d, p);
+  end_timing(c);
+  return rc;
+}
+
+int mfb_col_sqnorms(mfb_ctx* h, double* normu, double* normv, double* bu2, double* bv2) {
+  MFB_REQUIRE(h && normu && normv && bu2 && bv2, "NULL argument");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  const int w = c->stride + 1;
+  if (!c->d_norms) MFB_CUDA(cudaMalloc(&c->d_norms, 2 * w * sizeof(double)));
+  begin_timing(c);
+  int rc = launch_col_sqnorms(c, c->d_norms);
+  end_timing(c);
+  if (rc) return rc;
+  std::vector<double> hb(2 * w);
+  MFB_CUDA(cudaMemcpyAsync(hb.data(), c->d_norms, 2 * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->dim; i++) {
+    normu[i] = hb[i];
+    normv[i] = hb[w + i];
+  }
+  *bu2 = hb[c->stride];
+  *bv2 = hb[w + c->stride];
+  return MFB_OK;
+}
+
+int mfb_set_noise_table(mfb_ctx* h, const float* host, int64_t n) {
+  MFB_REQUIRE(h && host && n > 0, "bad argument");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_noise_table);
+  c->d_noise_table = nullptr;
+  MFB_CUDA(cudaMalloc(&c->d_noise_table, n * sizeof(float)));
+  MFB_CUDA(cudaMemcpy(c->d_noise_table, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  c->noise_table_size = n;
   return MFB_OK;
 }
 

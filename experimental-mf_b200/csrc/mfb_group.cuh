@@ -57,6 +57,46 @@ __device__ __forceinline__ void store_row(float* base, int64_t row, int nvec, in
   }
 }
 
+// Row access flavours (chosen per kernel launch; see DESIGN.md "memory operations"):
+//   0  ld/st.global.cg      -> SASS LDG/STG.E.128.STRONG.GPU (performed at the home L2 slice)
+//   1  plain ld/st.global   -> weak; loads may allocate and hit in L1 (stale reads possible)
+//   2  ld.global.L1::no_allocate / plain st -> weak but never resident in L1
+__device__ __forceinline__ float4 ld_na(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+template <int LPR, int VPL>
+__device__ __forceinline__ Row<VPL> load_row_f(const float* base, int64_t row, int nvec, int gl, int flavour) {
+  Row<VPL> r;
+  const float4* p = reinterpret_cast<const float4*>(base) + row * nvec;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int v = gl + i * LPR;
+    if (v < nvec) {
+      r.v[i] = flavour == 0 ? __ldcg(p + v) : (flavour == 1 ? p[v] : ld_na(p + v));
+    } else {
+      r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  return r;
+}
+template <int LPR, int VPL>
+__device__ __forceinline__ void store_row_f(float* base, int64_t row, int nvec, int gl,
+                                            const Row<VPL>& r, int flavour) {
+  float4* p = reinterpret_cast<float4*>(base) + row * nvec;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int v = gl + i * LPR;
+    if (v < nvec) {
+      if (flavour == 0) __stcg(p + v, r.v[i]);
+      else p[v] = r.v[i];
+    }
+  }
+}
+
 // row += r with one 128-bit fp32 reduction per vector (sm_90+: red.global.add.v4.f32)
 template <int LPR, int VPL>
 __device__ __forceinline__ void red_add_row(float* base, int64_t row, int nvec, int gl,

@@ -54,6 +54,8 @@ struct Dataset {
   int32_t* d_vc = nullptr;
   int32_t* d_last_u = nullptr;  // [nu]
   int32_t* d_last_v = nullptr;  // [nv]
+  std::vector<int32_t> h_ucount, h_vcount;  // records per user / item (dpmf weights)
+  double max_item_share = 0.0;              // records of the most rated item / all records
 };
 
 struct Context {
@@ -73,8 +75,15 @@ struct Context {
   std::vector<cudaEvent_t> chunk_events;
   bool timed = false;
   int64_t launches = 0;
+  // dpmf: optional emulation of the reference's noise_ table (ordered parity mode only)
+  float* d_noise_table = nullptr;
+  int64_t noise_table_size = 0;
+  double* d_norms = nullptr;  // [2*(stride+1)]
   // options
-  int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4;
+  int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
+  int opt_row_concurrency = 8;  // bound on simultaneous updates of the hottest item row (0 = none)
+  int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
+  int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
   std::vector<Dataset> datasets;
 };
 
@@ -82,12 +91,31 @@ int64_t array_rows(const Context* c, int which);
 int array_cols(const Context* c, int which);      // logical columns (dim or 1)
 int array_stride(const Context* c, int which);    // device row stride in floats
 
+// How many sub-warps may work at once.  Every sub-warp is, at any instant, updating one item row;
+// the hottest item (share p of all records) is therefore being updated by about W*p of them.
+// The reference runs at most --fly (default 8) SgdFilter calls at a time (main.cc:50,97); the
+// same bound is kept PER ROW here: W <= row_concurrency / p.  Without it thousands of sub-warps
+// read the same stale row: plain stores lose all but one update (measured: no convergence at ML-1M
+// shape) and atomic accumulation applies them all at once (measured: divergence).
+// Second bound: the user-runs in flight are a "mini-batch" whose members do not see each other's
+// updates; measured test-RMSE error vs the serial oracle grows with W / (runs in the file)
+// (0.09% -> 7e-5, 0.35% -> 2.6e-4, 0.7% -> 9e-4, 1.4% -> 3e-3), so W <= run_fraction * runs.
+struct LaunchShape {
+  int grid, threads;
+};
+LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
+                        double max_item_share, int64_t total_runs);
+
 // kernels (mfb_sgd.cu)
 // runs [run_begin, run_end) of the dataset, in the given schedule
 int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mode,
                int64_t run_begin, int64_t run_end);
 int launch_sse(Context* c, Dataset* d, float gb);
 int launch_fill_normal(Context* c, uint64_t seed, float scale);
+// kernels (mfb_sgld.cu)
+int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int mode);
+int launch_flush(Context* c, Dataset* d, const mfb_sgld_params* p);
+int launch_col_sqnorms(Context* c, double* d_out);
 
 // wire decoder (proto_wire.cc): appends every block of a [u32][mf.Block] file to the dataset
 int load_blocks_file(const char* path, Dataset* d);

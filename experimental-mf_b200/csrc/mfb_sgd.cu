@@ -31,6 +31,7 @@ struct SgdArgs {
   int* counter;
   int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
   float eta, lameta, lm1, gb;
+  int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
 };
 
 // One rating, fast arithmetic (fused multiply-adds, butterfly dot).
@@ -58,8 +59,13 @@ __device__ __forceinline__ void sgd_update_fast(const SgdArgs& a, Row<VPL>& t, f
     red_add_row<LPR, VPL>(a.phi, v, a.nvec, gl, nf);
     if (gl == 0) atomicAdd(a.bv + v, fmaf(a.lm1, bvv, e));
   } else {
-    store_row<LPR, VPL>(a.phi, v, a.nvec, gl, nf);
-    if (gl == 0) __stcg(a.bv + v, fmaf(a.lameta, bvv, e));
+    store_row_f<LPR, VPL>(a.phi, v, a.nvec, gl, nf, a.st_flavour);
+    // The item bias is a 4-byte word in a line shared by 32 items: plain stores to it serialise
+    // in L2 (measured: they alone doubled the epoch time), so it is updated with a reduction.
+    if (gl == 0) {
+      if (a.bias_flavour == 0) atomicAdd(a.bv + v, fmaf(a.lm1, bvv, e));
+      else if (a.bias_flavour == 2) __stcg(a.bv + v, fmaf(a.lameta, bvv, e));
+    }
   }
   bu = fmaf(a.lameta, bu, e);
 }
@@ -139,7 +145,8 @@ __global__ void __launch_bounds__(256) sgd_epoch_kernel(const SgdArgs a) {
         for (int b = 0; b < B; b++) {  // issue the B row gathers back to back
           v[b] = __shfl_sync(m, myvid, (b0 + b) & (LPR - 1), LPR);
           if (b0 + b < nb) {
-            f[b] = load_row<LPR, VPL>(a.phi, v[b], a.nvec, gl);
+            f[b] = ORDERED ? load_row<LPR, VPL>(a.phi, v[b], a.nvec, gl)
+                           : load_row_f<LPR, VPL>(a.phi, v[b], a.nvec, gl, a.ld_flavour);
             if (ORDERED) {
               bvv[b] = (gl == 0) ? __ldcg(a.bv + v[b]) : 0.f;
             } else {
@@ -251,32 +258,17 @@ __global__ void fill_normal_kernel(float* p, int64_t rows, int cols, int stride,
 // ------------------------------------------------------------------------------------------
 namespace {
 
-int pick_grid(Context* c, const void* kernel, int threads, int64_t groups_needed, int lpr) {
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
-  if (per_sm < 1) per_sm = 1;
-  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-  int64_t grid = (int64_t)c->sm_count * per_sm;  // persistent: a multiple of the SM count
-  const int groups_per_cta = threads / lpr;
-  const int64_t need = (groups_needed + groups_per_cta - 1) / groups_per_cta;
-  if (need < grid) grid = std::max<int64_t>(need, 1);
-  return (int)grid;
-}
-
 template <int LPR, int VPL>
-int launch_sgd_t(Context* c, const SgdArgs& a, int mode) {
-  const int threads = c->opt_threads;
-  dim3 grid, block(threads);
+int launch_sgd_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   if (mode == MFB_MODE_ORDERED) {
     sgd_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED, 1><<<1, 32, 0, c->stream>>>(a);
-  } else if (mode == MFB_MODE_ATOMIC) {
-    constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
-    auto k = sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>;
-    k<<<pick_grid(c, (const void*)k, threads, a.nruns - a.run_begin, LPR), threads, 0, c->stream>>>(a);
   } else {
     constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
-    auto k = sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
-    k<<<pick_grid(c, (const void*)k, threads, a.nruns - a.run_begin, LPR), threads, 0, c->stream>>>(a);
+    const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>
+                                            : (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
+    const LaunchShape ls = pick_launch(c, k, LPR, a.nruns - a.run_begin, d->max_item_share, d->nruns);
+    void* args[] = {(void*)&a};
+    MFB_CUDA(cudaLaunchKernel(k, dim3(ls.grid), dim3(ls.threads), args, 0, c->stream));
   }
   MFB_CUDA(cudaGetLastError());
   c->launches++;
@@ -286,7 +278,8 @@ int launch_sgd_t(Context* c, const SgdArgs& a, int mode) {
 template <int LPR, int VPL>
 int launch_sse_t(Context* c, const SseArgs& a) {
   auto k = sse_kernel<LPR, VPL>;
-  k<<<pick_grid(c, (const void*)k, 256, a.nruns, LPR), 256, 0, c->stream>>>(a);
+  const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, 0.0, 0);  // read-only: no bound
+  k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   MFB_CUDA(cudaGetLastError());
   c->launches++;
   return MFB_OK;
@@ -327,8 +320,11 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.lameta = (float)(1.0 - (double)(eta * lambda));  // mf.h:80
   a.lm1 = (float)((double)a.lameta - 1.0);           // mf.h:104
   a.gb = gb;
+  a.ld_flavour = c->opt_memopt & 3;
+  a.st_flavour = (c->opt_memopt >> 2) & 3;
+  a.bias_flavour = (c->opt_memopt >> 4) & 3;
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-#define CALL(L, V) return launch_sgd_t<L, V>(c, a, mode)
+#define CALL(L, V) return launch_sgd_t<L, V>(c, d, a, mode)
   MFB_DISPATCH_SHAPE(a.nvec, CALL);
 #undef CALL
   return MFB_OK;

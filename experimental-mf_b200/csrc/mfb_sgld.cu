@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
       const float r = __ldcs(a.rating + j);
       const int vc = __ldcs(a.vc + j);
       Row<VPL> f = load_row<LPR, VPL>(a.phi, v, a.nvec, gl);
+      const Row<VPL> f_in = f;
       float bvv = (gl == 0) ? __ldcg(a.bv + v) : 0.f;
+      const float bv_in = bvv;
       const float vr = __ldg(a.vr + v);
       const float av = -a.eta * vr * a.bound;                                     // dpmf.h:81
       const double cbv = 1.0 - (double)(a.eta * a.lambda_vb * vr * a.bound);      // dpmf.h:85
@@ -206,8 +208,8 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
           t.v[i] = tt;
           f.v[i] = ff;
         }
-        bu = (float)(cbu * (double)bu + (double)e);                        // dpmf.h:84
-        bvv = (float)(cbv * (double)bvv + (double)e);                      // dpmf.h:85
+        bu = (float)__dadd_rn(__dmul_rn(cbu, (double)bu), (double)e);      // dpmf.h:84 (unfused)
+        bvv = (float)__dadd_rn(__dmul_rn(cbv, (double)bvv), (double)e);    // dpmf.h:85
       } else {
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
@@ -236,8 +238,21 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
         bu = (float)(cbu * (double)bu + (double)e);
         bvv = (float)(cbv * (double)bvv + (double)e);
       }
-      store_row<LPR, VPL>(a.phi, v, a.nvec, gl, f);
-      if (gl == 0) __stcg(a.bv + v, bvv);
+      if (ORDERED) {
+        store_row<LPR, VPL>(a.phi, v, a.nvec, gl, f);
+        if (gl == 0) __stcg(a.bv + v, bvv);
+      } else {
+        // Parallel schedule: the item row receives its INCREMENT (noise + drift) as a 128-bit fp32
+        // reduction, so neither concurrent gradient steps nor concurrent noise injections are lost
+        // (a lost noise injection would break the temp*eta*ntrain variance invariant).
+        Row<VPL> df;
+#pragma unroll
+        for (int i = 0; i < VPL; i++)
+          df.v[i] = make_float4(f.v[i].x - f_in.v[i].x, f.v[i].y - f_in.v[i].y, f.v[i].z - f_in.v[i].z,
+                                f.v[i].w - f_in.v[i].w);
+        red_add_row<LPR, VPL>(a.phi, v, a.nvec, gl, df);
+        if (gl == 0) atomicAdd(a.bv + v, bvv - bv_in);
+      }
       uc = 1;  // consecutive records of a run are consecutive clock ticks
     }
     store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
@@ -316,20 +331,13 @@ __global__ void __launch_bounds__(256) col_sqnorm_kernel(const float* mat, const
 namespace {
 
 template <int LPR, int VPL>
-int launch_sgld_t(Context* c, const SgldArgs& a, int mode) {
-  const int threads = 256;
+int launch_sgld_t(Context* c, const Dataset* d, const SgldArgs& a, int mode) {
   if (mode == MFB_MODE_ORDERED) {
     sgld_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED><<<1, 32, 0, c->stream>>>(a);
   } else {
     auto k = sgld_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD>;
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0);
-    per_sm = std::max(per_sm, 1);
-    if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-    int64_t grid = (int64_t)c->sm_count * per_sm;
-    const int64_t need = ((int64_t)a.nruns + threads / LPR - 1) / (threads / LPR);
-    grid = std::max<int64_t>(1, std::min(grid, need));
-    k<<<(int)grid, threads, 0, c->stream>>>(a);
+    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns);
+    k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   }
   MFB_CUDA(cudaGetLastError());
   c->launches++;
@@ -392,7 +400,7 @@ int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int 
   a.table = p->use_table ? c->d_noise_table : nullptr;
   a.table_offset = p->table_offset;
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-#define CALL(L, V) return launch_sgld_t<L, V>(c, a, mode)
+#define CALL(L, V) return launch_sgld_t<L, V>(c, d, a, mode)
   MFB_DISPATCH_SHAPE(a.nvec, CALL);
 #undef CALL
   return MFB_OK;

@@ -67,6 +67,13 @@ SIGNATURES = {
     "mfb_sse": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mfb_seteta": (C.c_float, [C.c_float, C.c_int, C.c_float]),
     "mfb_seteta_cutoff": (C.c_float, [C.c_float, C.c_int, C.c_float, C.c_float]),
+    "mfb_dp_weights": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "mfb_dp_bound": (C.c_float, [C.c_float, C.c_int, C.c_int]),
+    "mfb_sgld_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int]),
+    "mfb_sgld_flush_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mfb_col_sqnorms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mfb_set_noise_table": (C.c_int, [C.c_void_p, f32p, C.c_int64]),
     "mfb_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "mfb_launch_count": (C.c_int64, [C.c_void_p]),
 }
@@ -108,6 +115,14 @@ class GenParams(C.Structure):
                 ("zipf_s", C.c_float), ("test_frac", C.c_float), ("valid_frac", C.c_float),
                 ("split", C.c_int32), ("users_per_block", C.c_int32), ("seed", C.c_uint64),
                 ("user_begin", C.c_int32), ("user_end", C.c_int32), ("threads", C.c_int32)]
+
+
+class SgldParams(C.Structure):
+    """mfb_sgld_params (include/mf_b200.h)."""
+    _fields_ = [("eta", C.c_float), ("temp", C.c_float), ("bound", C.c_float), ("ntrain", C.c_int32),
+                ("lambda_r", C.c_float), ("lambda_ub", C.c_float), ("lambda_vb", C.c_float),
+                ("seed", C.c_uint64), ("round", C.c_uint32), ("use_table", C.c_int32),
+                ("table_offset", C.c_int32)]
 
 
 class Blocks:
@@ -331,6 +346,30 @@ class Context:
 
     def sgd_epoch_from_host(self, ds, blocks, eta, lam, gb, mode=MODE_HOGWILD, chunk_ratings=0):
         _check(lib().mfb_sgd_epoch_from_host(self.h, ds, blocks.h, eta, lam, gb, mode, chunk_ratings))
+
+    # -- dpmf
+    def dp_weights(self, ds):
+        n = C.c_int32()
+        _check(lib().mfb_dp_weights(self.h, ds, C.byref(n)))
+        return n.value
+
+    def sgld_epoch(self, ds, params, gb, mode=MODE_HOGWILD):
+        _check(lib().mfb_sgld_epoch(self.h, ds, C.byref(params), gb, mode))
+
+    def sgld_flush_noise(self, ds, params):
+        _check(lib().mfb_sgld_flush_noise(self.h, ds, C.byref(params)))
+
+    def col_sqnorms(self):
+        nu_, nv_ = np.zeros(self.dim), np.zeros(self.dim)
+        bu2, bv2 = C.c_double(), C.c_double()
+        dp = C.POINTER(C.c_double)
+        _check(lib().mfb_col_sqnorms(self.h, nu_.ctypes.data_as(dp), nv_.ctypes.data_as(dp),
+                                     C.byref(bu2), C.byref(bv2)))
+        return nu_, nv_, bu2.value, bv2.value
+
+    def set_noise_table(self, table):
+        t = _f32(table)
+        _check(lib().mfb_set_noise_table(self.h, t.ctypes.data_as(f32p), len(t)))
 
     def sse(self, ds, gb):
         s, n = C.c_double(), C.c_int64()

