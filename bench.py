@@ -44,6 +44,16 @@ def bytes_per_update(k):
     return 12 + 16 * k  # rating record + two factor rows read and written
 
 
+def profiled_traffic(schedule):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the update kernel, from the
+    committed ncu --set full capture of this same command (profiles/, made by tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "r1_sgd_%s.json" % schedule)
+    try:
+        return float(json.load(open(p))["launches"][0]["dram_traffic_bytes"]), os.path.relpath(p, ROOT)
+    except (OSError, KeyError, IndexError, ValueError):
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -256,6 +266,7 @@ def run_b200_arm(args, wl):
     ms_per_step = total_ms / args.steps
     value = ntrain * args.steps / (total_ms * 1e-3)
     peak, peak_src = measured_peak()
+    traffic, traffic_src = profiled_traffic(args.schedule) if wl == "netflix" else (None, None)
     kavg = sum(kern_ms) / len(kern_ms)
     achieved = ntrain * bytes_per_update(k) / (kavg * 1e-3) / 1e9
     rmse_resident = c.rmse(dte, GB)
@@ -301,7 +312,7 @@ def run_b200_arm(args, wl):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "sgd_epoch_kernel<LPR=32,VPL=1,%s>" % args.schedule if k == 128 else "sgd_epoch_kernel",
                      "kernel_ms": kavg, "bytes_per_update": bytes_per_update(k), "updates_per_launch": ntrain,
                      "note": "algorithmic bytes; theta rows stay in registers across a user-run and phi rows are "

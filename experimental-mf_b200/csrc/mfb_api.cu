@@ -204,6 +204,8 @@ void mfb_destroy(mfb_ctx* h) {
   cudaFree(c->d_accum);
   cudaFree(c->d_noise_table);
   cudaFree(c->d_norms);
+  cudaFree(c->d_val_u); cudaFree(c->d_val_v); cudaFree(c->d_val_r);
+  cudaFree(c->d_draws); cudaFree(c->d_lams);
   cudaFreeHost(c->h_accum);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -702,6 +704,95 @@ int mfb_set_noise_table(mfb_ctx* h, const float* host, int64_t n) {
   MFB_CUDA(cudaMemcpy(c->d_noise_table, host, n * sizeof(float), cudaMemcpyHostToDevice));
   c->noise_table_size = n;
   return MFB_OK;
+}
+
+// ---- admf ------------------------------------------------------------------------------------
+int mfb_admf_set_validation(mfb_ctx* h, int64_t n, const int32_t* u, const int32_t* v, const float* r) {
+  MFB_REQUIRE(h && n > 0 && u && v && r, "bad argument");
+  Context* c = &h->c;
+  for (int64_t i = 0; i < n; i++)
+    MFB_REQUIRE(u[i] >= 0 && u[i] < c->nu && v[i] >= 0 && v[i] < c->nv, "validation record %lld out of range", (long long)i);
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_val_u); cudaFree(c->d_val_v); cudaFree(c->d_val_r);
+  c->d_val_u = c->d_val_v = nullptr;
+  c->d_val_r = nullptr;
+  MFB_CUDA(cudaMalloc(&c->d_val_u, n * sizeof(int32_t)));
+  MFB_CUDA(cudaMalloc(&c->d_val_v, n * sizeof(int32_t)));
+  MFB_CUDA(cudaMalloc(&c->d_val_r, n * sizeof(float)));
+  MFB_CUDA(cudaMemcpy(c->d_val_u, u, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  MFB_CUDA(cudaMemcpy(c->d_val_v, v, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  MFB_CUDA(cudaMemcpy(c->d_val_r, r, n * sizeof(float), cudaMemcpyHostToDevice));
+  c->nvalid = n;
+  return MFB_OK;
+}
+
+int mfb_admf_set_draws(mfb_ctx* h, int64_t n, const int32_t* draws) {
+  MFB_REQUIRE(h && n >= 0 && (n == 0 || draws), "bad argument");
+  Context* c = &h->c;
+  MFB_REQUIRE(c->nvalid > 0, "set the validation list first");
+  for (int64_t i = 0; i < n; i++) MFB_REQUIRE(draws[i] >= 0 && draws[i] < c->nvalid, "draw %lld out of range", (long long)i);
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (n > c->ndraws) {
+    MFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_draws);
+    c->d_draws = nullptr;
+    MFB_CUDA(cudaMalloc(&c->d_draws, std::max<int64_t>(n, 1) * sizeof(int32_t)));
+  }
+  c->ndraws = n;
+  if (n) MFB_CUDA(cudaMemcpyAsync(c->d_draws, draws, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  return MFB_OK;
+}
+
+static int ensure_lams(Context* c) {
+  if (!c->d_lams) {
+    MFB_CUDA(cudaMalloc(&c->d_lams, 4 * sizeof(float)));
+    MFB_CUDA(cudaMemsetAsync(c->d_lams, 0, 4 * sizeof(float), c->stream));
+  }
+  return MFB_OK;
+}
+
+int mfb_admf_set_lams(mfb_ctx* h, const float lams[4]) {
+  MFB_REQUIRE(h && lams, "NULL argument");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_lams(c);
+  if (rc) return rc;
+  MFB_CUDA(cudaMemcpyAsync(c->d_lams, lams, 4 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  return MFB_OK;
+}
+
+int mfb_admf_get_lams(mfb_ctx* h, float lams[4]) {
+  MFB_REQUIRE(h && lams, "NULL argument");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_lams(c);
+  if (rc) return rc;
+  MFB_CUDA(cudaMemcpyAsync(lams, c->d_lams, 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 4; k++) lams[k] = lams[k] < 0.f ? 0.f : lams[k];  // clamped view (model.h:94)
+  return MFB_OK;
+}
+
+int mfb_admf_epoch(mfb_ctx* h, int ds, float eta, float eta_reg, int loss, float gb, int mode) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_REQUIRE(c->arr[MFB_THETA_OLD], "admf shadows not enabled (mfb_enable(ctx, 1))");
+  MFB_REQUIRE(c->nvalid > 0 && c->d_lams, "validation list / regularisers not set");
+  MFB_REQUIRE(c->ndraws >= d->nruns, "need one validation draw per user-run (%lld < %lld)",
+              (long long)c->ndraws, (long long)d->nruns);
+  MFB_REQUIRE(mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC || mode == MFB_MODE_HOGWILD, "bad mode %d", mode);
+  MFB_REQUIRE(loss == 0 || loss == 1, "loss must be 0 (least squares) or 1 (logistic)");
+  MFB_CUDA(cudaSetDevice(c->device));
+  begin_timing(c);
+  int rc = d->nruns ? launch_admf(c, d, eta, eta_reg, loss, gb, mode) : MFB_OK;
+  end_timing(c);
+  return rc;
 }
 
 float mfb_last_kernel_ms(mfb_ctx* h) {

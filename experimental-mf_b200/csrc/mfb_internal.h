@@ -79,6 +79,14 @@ struct Context {
   float* d_noise_table = nullptr;
   int64_t noise_table_size = 0;
   double* d_norms = nullptr;  // [2*(stride+1)]
+  // admf: validation records, per-run draws, the four regularisers
+  int32_t* d_val_u = nullptr;
+  int32_t* d_val_v = nullptr;
+  float* d_val_r = nullptr;
+  int64_t nvalid = 0;
+  int32_t* d_draws = nullptr;
+  int64_t ndraws = 0;
+  float* d_lams = nullptr;  // [4]
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
   int opt_row_concurrency = 8;  // bound on simultaneous updates of the hottest item row (0 = none)
@@ -116,6 +124,8 @@ int launch_fill_normal(Context* c, uint64_t seed, float scale);
 int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int mode);
 int launch_flush(Context* c, Dataset* d, const mfb_sgld_params* p);
 int launch_col_sqnorms(Context* c, double* d_out);
+// kernels (mfb_admf.cu)
+int launch_admf(Context* c, Dataset* d, float eta, float eta_reg, int loss, float gb, int mode);
 
 // wire decoder (proto_wire.cc): appends every block of a [u32][mf.Block] file to the dataset
 int load_blocks_file(const char* path, Dataset* d);

@@ -74,6 +74,11 @@ SIGNATURES = {
     "mfb_col_sqnorms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mfb_set_noise_table": (C.c_int, [C.c_void_p, f32p, C.c_int64]),
+    "mfb_admf_set_validation": (C.c_int, [C.c_void_p, C.c_int64, i32p, i32p, f32p]),
+    "mfb_admf_set_draws": (C.c_int, [C.c_void_p, C.c_int64, i32p]),
+    "mfb_admf_set_lams": (C.c_int, [C.c_void_p, f32p]),
+    "mfb_admf_get_lams": (C.c_int, [C.c_void_p, f32p]),
+    "mfb_admf_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]),
     "mfb_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "mfb_launch_count": (C.c_int64, [C.c_void_p]),
 }
@@ -370,6 +375,28 @@ class Context:
     def set_noise_table(self, table):
         t = _f32(table)
         _check(lib().mfb_set_noise_table(self.h, t.ctypes.data_as(f32p), len(t)))
+
+    # -- admf
+    def admf_set_validation(self, u, v, r):
+        u, v, r = np.ascontiguousarray(u, np.int32), np.ascontiguousarray(v, np.int32), _f32(r)
+        _check(lib().mfb_admf_set_validation(self.h, len(u), u.ctypes.data_as(i32p), v.ctypes.data_as(i32p),
+                                             r.ctypes.data_as(f32p)))
+
+    def admf_set_draws(self, draws):
+        d = np.ascontiguousarray(draws, np.int32)
+        _check(lib().mfb_admf_set_draws(self.h, len(d), d.ctypes.data_as(i32p)))
+
+    def admf_set_lams(self, lams):
+        a = _f32(lams)
+        _check(lib().mfb_admf_set_lams(self.h, a.ctypes.data_as(f32p)))
+
+    def admf_get_lams(self):
+        a = np.zeros(4, np.float32)
+        _check(lib().mfb_admf_get_lams(self.h, a.ctypes.data_as(f32p)))
+        return a
+
+    def admf_epoch(self, ds, eta, eta_reg, loss, gb, mode=MODE_ATOMIC):
+        _check(lib().mfb_admf_epoch(self.h, ds, eta, eta_reg, loss, gb, mode))
 
     def sse(self, ds, gb):
         s, n = C.c_double(), C.c_int64()

@@ -199,6 +199,21 @@ int mfb_col_sqnorms(mfb_ctx* ctx, double* normu, double* normv, double* bu2, dou
 /* upload a stand-in for the reference's noise_ lookup table (model.cc:229-231); parity tests only */
 int mfb_set_noise_table(mfb_ctx* ctx, const float* host, int64_t n);
 
+/* ---- admf: adaptive regulariser (Rendle) ------------------------------------------------------
+ * Needs mfb_enable(ctx, 1) (the *_OLD shadows; mfb_snapshot_old() is AdaptRegMF::init1's copy).
+ * set_validation: the flattened, already shuffled validation list recsv_ (model.cc:390-415).
+ * set_draws: for the next epoch, one index into that list per user-run in file order - the host
+ * draws them with rand() % |valid| exactly as admf.h:82 does, so the sequence is the reference's.
+ * lams: lam_u_, lam_v_, lam_bu_, lam_bv_ (model.h:111-117), all initialised to --lambda. */
+int mfb_admf_set_validation(mfb_ctx* ctx, int64_t n, const int32_t* u, const int32_t* v, const float* r);
+int mfb_admf_set_draws(mfb_ctx* ctx, int64_t n, const int32_t* draws);
+int mfb_admf_set_lams(mfb_ctx* ctx, const float lams[4]);
+int mfb_admf_get_lams(mfb_ctx* ctx, float lams[4]);
+/* AdRegFilter::operator() over every block (admf.h:52-86) + updateReg after every user
+ * (model.h:86-102); eta_reg = AdaptRegMF::set_etareg's value (model.cc:386-388);
+ * mode ORDERED (serial, exact lambda trajectory) or ATOMIC (parallel) */
+int mfb_admf_epoch(mfb_ctx* ctx, int ds, float eta, float eta_reg, int loss, float gb, int mode);
+
 /* device time in ms of the most recent epoch / sse call's kernels (CUDA events on the
  * context's stream; valid after mfb_sync) and the number of kernel launches since create */
 float mfb_last_kernel_ms(mfb_ctx* ctx);

@@ -1,0 +1,139 @@
+"""admf path (adaptive regulariser) on the GPU through the C ABI: the ordered mode against the
+reference's golden outputs (factors, *_old shadows and the lambda trajectory), the parallel mode
+against the serial oracle on RMSE and on the final regularisers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mfb200 as mb
+import oraclelib as ol
+from gpu_common import ctx_from_model, model_rel_err, row_rel_err, upload_ds, vec_rel_err
+from oraclelib import MfoAdState, _p, f32p, i32p
+from test_oracle_golden import init_model, load_ds
+
+pytestmark = pytest.mark.gpu
+GB = 2.76
+
+
+def glibc_draws(seed, nvalid, nruns_per_epoch, epochs, vu, vv, vr):
+    """The reference's rand() stream: srand(seed); std::random_shuffle of the validation list
+    (model.cc:413) and then one rand() % nvalid per user-run (admf.h:82)."""
+    libc = C.CDLL("libc.so.6")
+    L = ol.oracle()
+    L.mfo_srand(seed)
+    L.mfo_shuffle_valid(len(vu), _p(vu, i32p), _p(vv, i32p), _p(vr, f32p))
+    return [np.array([libc.rand() % nvalid for _ in range(nruns_per_epoch)], np.int32) for _ in range(epochs)]
+
+
+@pytest.mark.parametrize("loss", [0, 1])
+def test_ordered_admf_reproduces_reference_golden(golden, loss):
+    g = golden
+    m, train, valid, test = init_model(g), load_ds(g, "train"), load_ds(g, "valid"), load_ds(g, "test")
+    eta0, gam, lam, eta_reg0 = [np.float32(x) for x in g["ad_params"]]
+    gb = float(g["gb"])
+    vu, vv, vr = valid.uid_per_rating().copy(), valid.vid.copy(), valid.rating.copy()
+    draws = glibc_draws(int(g["ad_seed"]), len(vu), train.nruns, 3, vu, vv, vr)
+    np.testing.assert_array_equal(vu, g["ad_valid_u"])
+    c = ctx_from_model(m)
+    c.enable(1)
+    c.snapshot_old()  # AdaptRegMF::init1, model.cc:369-382
+    d, dte = upload_ds(c, train), upload_ds(c, test)
+    c.admf_set_validation(vu, vv, vr)
+    c.admf_set_lams([lam] * 4)
+    k = "ad%d_" % loss
+    for ep in (1, 2, 3):
+        c.admf_set_draws(draws[ep - 1])
+        c.admf_epoch(d, mb.seteta(eta0, ep, gam), mb.seteta(eta_reg0, ep, gam), loss, gb, mb.MODE_ORDERED)
+        lams = c.admf_get_lams()
+        got = {"theta": c.download(mb.THETA), "phi": c.download(mb.PHI), "bu": c.download(mb.BU),
+               "bv": c.download(mb.BV), "theta_old": c.download(mb.THETA_OLD), "phi_old": c.download(mb.PHI_OLD),
+               "bu_old": c.download(mb.BU_OLD), "bv_old": c.download(mb.BV_OLD)}
+        if loss == 0:  # identity link: bit-exact, including the lambda trajectory
+            np.testing.assert_array_equal(lams, g[k + "lams_%d" % ep])
+            for name, a in got.items():
+                np.testing.assert_array_equal(a, g[k + "%s_%d" % (name, ep)], err_msg=name)
+        else:  # logistic link goes through expf of two different libms
+            np.testing.assert_allclose(lams, g[k + "lams_%d" % ep], rtol=1e-5, atol=1e-9)
+            for name in ("theta", "phi", "theta_old", "phi_old"):
+                assert row_rel_err(got[name], g[k + "%s_%d" % (name, ep)]) <= 1e-5, name
+            for name in ("bu", "bv", "bu_old", "bv_old"):
+                assert vec_rel_err(got[name], g[k + "%s_%d" % (name, ep)]) <= 1e-5, name
+        s, _ = c.sse(dte, gb)
+        assert abs(s - float(g[k + "test_sse_%d" % ep])) <= 1e-5 * s
+    c.close()
+
+
+@pytest.mark.parametrize("dim", [16, 32, 64, 128, 200])
+def test_ordered_admf_bit_exact_vs_oracle_all_row_shapes(dim):
+    L = ol.oracle()
+    nu, nv = 120, 80
+    train, _, valid = ol.make_ratings(nu, nv, 4000, seed=dim, valid_frac=0.05)
+    m = ol.Model(nu, nv, dim, seed=3, scale=0.1)
+    vu, vv, vr = valid.uid_per_rating().copy(), valid.vid.copy(), valid.rating.copy()
+    rng = np.random.default_rng(dim)
+    c = ctx_from_model(m)
+    c.enable(1)
+    c.snapshot_old()
+    d = upload_ds(c, train)
+    c.admf_set_validation(vu, vv, vr)
+    c.admf_set_lams([5e-3] * 4)
+    tho, pho, buo, bvo = m.theta.copy(), m.phi.copy(), m.bu.copy(), m.bv.copy()
+    st = MfoAdState(0, 0, 0, 5e-3, 5e-3, 5e-3, 5e-3, _p(tho, f32p), _p(pho, f32p), _p(buo, f32p), _p(bvo, f32p),
+                    len(vu), _p(vu, i32p), _p(vv, i32p), _p(vr, f32p), None, 0)
+    mm, dd = m.as_mfo(), train.as_mfo()
+    for ep in (1, 2):
+        draws = rng.integers(0, len(vu), train.nruns).astype(np.int32)
+        c.admf_set_draws(draws)
+        eta, eta_reg = mb.seteta(3e-2, ep, 1.0), mb.seteta(0.5, ep, 1.0)
+        c.admf_epoch(d, eta, eta_reg, 0, GB, mb.MODE_ORDERED)
+        st.eta, st.eta_reg, st.draws, st.draw_pos = eta, eta_reg, _p(draws, i32p), 0
+        L.mfo_admf_epoch(C.byref(mm), C.byref(dd), C.byref(st), GB)
+        np.testing.assert_array_equal(c.admf_get_lams(), np.array([st.lam_u, st.lam_v, st.lam_bu, st.lam_bv], np.float32))
+        assert model_rel_err(c, m) == 0.0
+        np.testing.assert_array_equal(c.download(mb.THETA_OLD), tho[:, :dim])
+        np.testing.assert_array_equal(c.download(mb.PHI_OLD), pho[:, :dim])
+    c.close()
+
+
+def test_parallel_admf_tracks_serial_oracle_ml1m_shape():
+    """configs[3] flavour at a size the oracle runs in seconds: RMSE and the four regularisers of
+    the parallel schedule vs the serial oracle fed the same validation draws."""
+    L = ol.oracle()
+    nu, nv, dim, epochs = 6040, 3706, 32, 8
+    tr, te, va = mb.generate(mb.gen_params(nu, nv, 1_000_000, test_frac=0.1, valid_frac=0.02))
+    train = ol.Dataset(tr.block_off, tr.run_uid, tr.run_off, tr.vid, tr.rating)
+    test = ol.Dataset(te.block_off, te.run_uid, te.run_off, te.vid, te.rating)
+    vu = np.repeat(va.run_uid, np.diff(va.run_off)).astype(np.int32)
+    vv, vr = va.vid.copy(), va.rating.copy()
+    m = ol.Model(nu, nv, dim, seed=11)
+    c = ctx_from_model(m)
+    c.enable(1)
+    c.snapshot_old()
+    d, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+    c.admf_set_validation(vu, vv, vr)
+    c.admf_set_lams([5e-3] * 4)
+    tho, pho, buo, bvo = m.theta.copy(), m.phi.copy(), m.bu.copy(), m.bv.copy()
+    st = MfoAdState(0, 0, 0, 5e-3, 5e-3, 5e-3, 5e-3, _p(tho, f32p), _p(pho, f32p), _p(buo, f32p), _p(bvo, f32p),
+                    len(vu), _p(vu, i32p), _p(vv, i32p), _p(vr, f32p), None, 0)
+    mm, dd, tt = m.as_mfo(), train.as_mfo(), test.as_mfo()
+    rng = np.random.default_rng(0)
+    got, want, lg, lw = [], [], [], []
+    for ep in range(1, epochs + 1):
+        draws = rng.integers(0, len(vu), train.nruns).astype(np.int32)
+        eta, eta_reg = mb.seteta(2e-2, ep, 1.0), mb.seteta(2e-2, ep, 1.0)
+        c.admf_set_draws(draws)
+        c.admf_epoch(d, eta, eta_reg, 0, GB, mb.MODE_ATOMIC)
+        got.append(c.rmse(dte, GB))
+        lg.append(c.admf_get_lams())
+        st.eta, st.eta_reg, st.draws, st.draw_pos = eta, eta_reg, _p(draws, i32p), 0
+        L.mfo_admf_epoch(C.byref(mm), C.byref(dd), C.byref(st), GB)
+        n = C.c_int64()
+        s = L.mfo_sse(C.byref(mm), C.byref(tt), GB, C.byref(n))
+        want.append(float(np.sqrt(s / n.value)))
+        lw.append(np.array([st.lam_u, st.lam_v, st.lam_bu, st.lam_bv]))
+    print("admf oracle  rmse", ["%.4f" % x for x in want], "lams", lw[-1])
+    print("admf parallel rmse", ["%.4f" % x for x in got], "lams", lg[-1])
+    assert abs(got[-1] - want[-1]) <= 2e-3
+    np.testing.assert_allclose(lg[-1], lw[-1], rtol=0.1, atol=2e-4)
+    c.close()
