@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 #include "mfb_internal.h"
@@ -84,6 +85,39 @@ int mfb_blocks_write(const mfb_blocks* b, const char* path) {
     set_error("close failed on %s", path);
     return MFB_E_IO;
   }
+  return MFB_OK;
+}
+
+// DSGD strata: part j keeps the records whose item lies in [bounds[j], bounds[j+1]), with the
+// user-runs (and Block boundaries) of the source file; runs left without records are dropped.
+int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bounds, mfb_blocks** out) {
+  MFB_REQUIRE(b && bounds && out && nparts >= 1, "bad argument");
+  for (int j = 0; j < nparts; j++) MFB_REQUIRE(bounds[j] <= bounds[j + 1], "bounds must be non-decreasing");
+  const Dataset& d = b->d;
+  std::vector<mfb_blocks*> parts(nparts);
+  for (auto& p : parts) p = blocks_new();
+  const int64_t nblocks = (int64_t)d.h_block_off.size() - 1;
+  std::vector<int32_t> start(nparts);
+  for (int64_t k = 0; k < nblocks; k++) {
+    for (int64_t r = d.h_block_off[k]; r < d.h_block_off[k + 1]; r++) {
+      for (int j = 0; j < nparts; j++) start[j] = (int32_t)parts[j]->d.h_vid.size();
+      for (int32_t t = d.h_run_off[r]; t < d.h_run_off[r + 1]; t++) {
+        const int32_t v = d.h_vid[t];
+        const int j = (int)(std::upper_bound(bounds, bounds + nparts + 1, v) - bounds) - 1;
+        if (j < 0 || j >= nparts) continue;  // item outside every part
+        parts[j]->d.h_vid.push_back(v);
+        parts[j]->d.h_rating.push_back(d.h_rating[t]);
+      }
+      for (int j = 0; j < nparts; j++) {
+        Dataset& o = parts[j]->d;
+        if ((int32_t)o.h_vid.size() == start[j]) continue;
+        o.h_run_uid.push_back(d.h_run_uid[r]);
+        o.h_run_off.push_back((int32_t)o.h_vid.size());
+      }
+    }
+    for (int j = 0; j < nparts; j++) parts[j]->d.h_block_off.push_back((int64_t)parts[j]->d.h_run_uid.size());
+  }
+  for (int j = 0; j < nparts; j++) out[j] = parts[j];
   return MFB_OK;
 }
 

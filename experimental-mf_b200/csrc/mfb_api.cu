@@ -93,6 +93,8 @@ static Dataset* get_ds(Context* c, int ds) {
 }
 
 static void free_ds_device(Dataset* d) {
+  if (d->refreshed) cudaEventDestroy(d->refreshed);
+  d->refreshed = nullptr;
   cudaFree(d->d_run_uid); cudaFree(d->d_run_off); cudaFree(d->d_vid); cudaFree(d->d_rating);
   cudaFree(d->d_uc); cudaFree(d->d_vc); cudaFree(d->d_last_u); cudaFree(d->d_last_v);
   d->d_run_uid = d->d_run_off = d->d_vid = nullptr;
@@ -196,6 +198,7 @@ int mfb_create(mfb_ctx** out, int device, int nu, int nv, int dim) {
 void mfb_destroy(mfb_ctx* h) {
   if (!h) return;
   Context* c = &h->c;
+  mfb_comm_destroy(h);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& d : c->datasets) free_ds_device(&d);
@@ -551,6 +554,37 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
     r0 = r1;
   }
   end_timing(c);
+  return MFB_OK;
+}
+
+// Re-send the tiles of a finalized dataset from (pinned) host arrays: H2D on the copy stream; the
+// next kernel that uses the dataset waits for it.  Lets several datasets (the DSGD cells of one
+// epoch) stream in behind the compute of the previous ones.
+int mfb_dataset_refresh_from_host(mfb_ctx* h, int ds, const mfb_blocks* src) {
+  MFB_REQUIRE(h && src, "NULL argument");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  const Dataset* s = blocks_data(src);
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_REQUIRE((int64_t)s->h_run_uid.size() == d->nruns && (int64_t)s->h_vid.size() == d->nratings,
+              "host blocks do not match dataset %d", ds);
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!d->refreshed) MFB_CUDA(cudaEventCreateWithFlags(&d->refreshed, cudaEventDisableTiming));
+  // do not overwrite tiles that kernels already queued on the main stream still read
+  MFB_CUDA(cudaEventRecord(d->refreshed, c->stream));
+  MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, d->refreshed, 0));
+  if (d->nruns) {
+    MFB_CUDA(cudaMemcpyAsync(d->d_run_uid, s->h_run_uid.data(), d->nruns * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(d->d_run_off, s->h_run_off.data(), (d->nruns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  if (d->nratings) {
+    MFB_CUDA(cudaMemcpyAsync(d->d_vid, s->h_vid.data(), d->nratings * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(d->d_rating, s->h_rating.data(), d->nratings * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  MFB_CUDA(cudaEventRecord(d->refreshed, c->copy_stream));
+  d->refresh_pending = true;
   return MFB_OK;
 }
 

@@ -1,0 +1,211 @@
+// C1: DSGD stratification over the GPUs of one NVSwitch box.  New design - the
+// reference has no multi-process path.
+//
+// One process per GPU.  Users are sharded by rank: rank p owns theta/bu of its users and all of
+// their ratings, pre-split by item block.  Items are cut into P blocks.  An epoch is P
+// sub-epochs: in sub-epoch s rank p updates cell (p, b = (p+s) mod P) with block b of phi/bv
+// resident, then hands block b to rank p-1 and receives block b+1 from rank p+1 (a ring shift over
+// NVLink, ncclSend/ncclRecv inside one group on a dedicated stream).  Cells that run at the same
+// time share neither users nor items, so there is no inter-GPU conflict; inside a cell the
+// schedule is the single-GPU one.  After P shifts every block is home again.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+
+#include "mfb_internal.h"
+
+namespace mfb {
+
+// NCCL is bound at run time (dlopen), not at link time: the library then loads on machines
+// without NCCL, and inside a PyTorch process it shares the libnccl.so.2 torch already mapped
+// instead of pulling a second copy with the same SONAME.  MFB_NCCL_LIB overrides the path.
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return MFB_OK;
+  const char* path = getenv("MFB_NCCL_LIB");
+  void* h = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("cannot load NCCL: %s", dlerror());
+    return MFB_E_COMM;
+  }
+#define MFB_SYM(name)                                                   \
+  g_nccl.name = (decltype(g_nccl.name))dlsym(h, "nccl" #name);          \
+  if (!g_nccl.name) {                                                   \
+    set_error("NCCL symbol nccl" #name " missing");                     \
+    return MFB_E_COMM;                                                  \
+  }
+  MFB_SYM(GetUniqueId) MFB_SYM(CommInitRank) MFB_SYM(CommDestroy) MFB_SYM(GroupStart) MFB_SYM(GroupEnd)
+  MFB_SYM(Send) MFB_SYM(Recv) MFB_SYM(Broadcast) MFB_SYM(AllReduce) MFB_SYM(GetErrorString)
+#undef MFB_SYM
+  g_nccl.handle = h;
+  return MFB_OK;
+}
+
+#define MFB_NCCL(expr)                                                                    \
+  do {                                                                                    \
+    ncclResult_t _r = (expr);                                                             \
+    if (_r != ncclSuccess) {                                                              \
+      set_error("%s:%d %s: %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(_r));       \
+      return MFB_E_COMM;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+struct Comm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t computed = nullptr, shifted = nullptr;
+  double* d_red = nullptr;  // [2] sse, count
+};
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" {
+
+int mfb_comm_unique_id(void* out128) {
+  MFB_REQUIRE(out128, "NULL argument");
+  if (int rc = load_nccl()) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  MFB_NCCL(g_nccl.GetUniqueId((ncclUniqueId*)out128));
+  return MFB_OK;
+}
+
+int mfb_comm_init(mfb_ctx* h, int rank, int world, const void* id128) {
+  MFB_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world, "bad argument");
+  Context* c = &h->c;
+  MFB_REQUIRE(!c->comm, "communicator already initialised");
+  if (int rc = load_nccl()) return rc;
+  MFB_CUDA(cudaSetDevice(c->device));
+  Comm* m = new Comm();
+  m->rank = rank;
+  m->world = world;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  MFB_NCCL(g_nccl.CommInitRank(&m->nccl, world, id, rank));
+  MFB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  MFB_CUDA(cudaEventCreateWithFlags(&m->computed, cudaEventDisableTiming));
+  MFB_CUDA(cudaEventCreateWithFlags(&m->shifted, cudaEventDisableTiming));
+  MFB_CUDA(cudaMalloc(&m->d_red, 2 * sizeof(double)));
+  c->comm = m;
+  return MFB_OK;
+}
+
+int mfb_comm_destroy(mfb_ctx* h) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  if (!m) return MFB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(m->stream);
+  cudaStreamSynchronize(c->stream);
+  if (m->nccl) g_nccl.CommDestroy(m->nccl);
+  cudaEventDestroy(m->computed);
+  cudaEventDestroy(m->shifted);
+  cudaStreamDestroy(m->stream);
+  cudaFree(m->d_red);
+  delete m;
+  c->comm = nullptr;
+  return MFB_OK;
+}
+
+// ring shift of one item block: send rows [bounds[b], bounds[b+1]) of phi/bv to rank-1, receive
+// block nb from rank+1.  Runs on the comm stream after the compute stream reached `computed`.
+static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb) {
+  const int P = m->world;
+  const int to = (m->rank + P - 1) % P, from = (m->rank + 1) % P;
+  const int64_t s0 = bounds[b], s1 = bounds[b + 1], r0 = bounds[nb], r1 = bounds[nb + 1];
+  MFB_CUDA(cudaEventRecord(m->computed, c->stream));
+  MFB_CUDA(cudaStreamWaitEvent(m->stream, m->computed, 0));
+  MFB_NCCL(g_nccl.GroupStart());
+  MFB_NCCL(g_nccl.Send(c->arr[MFB_PHI] + s0 * c->stride, (size_t)(s1 - s0) * c->stride, ncclFloat, to, m->nccl, m->stream));
+  MFB_NCCL(g_nccl.Send(c->arr[MFB_BV] + s0, (size_t)(s1 - s0), ncclFloat, to, m->nccl, m->stream));
+  MFB_NCCL(g_nccl.Recv(c->arr[MFB_PHI] + r0 * c->stride, (size_t)(r1 - r0) * c->stride, ncclFloat, from, m->nccl, m->stream));
+  MFB_NCCL(g_nccl.Recv(c->arr[MFB_BV] + r0, (size_t)(r1 - r0), ncclFloat, from, m->nccl, m->stream));
+  MFB_NCCL(g_nccl.GroupEnd());
+  MFB_CUDA(cudaEventRecord(m->shifted, m->stream));
+  MFB_CUDA(cudaStreamWaitEvent(c->stream, m->shifted, 0));
+  return MFB_OK;
+}
+
+int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
+                   float gb, int mode) {
+  MFB_REQUIRE(h && datasets && item_bounds, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m, "communicator not initialised");
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC || mode == MFB_MODE_ORDERED, "bad mode");
+  const int P = m->world;
+  MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[P] == c->nv, "item_bounds must span [0, nv]");
+  MFB_CUDA(cudaSetDevice(c->device));
+  cudaEventRecord(c->ev0, c->stream);
+  for (int s = 0; s < P; s++) {
+    const int b = (m->rank + s) % P, nb = (b + 1) % P;
+    const int ds = datasets[b];
+    MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].finalized, "bad dataset for block %d", b);
+    Dataset* d = &c->datasets[ds];
+    if (d->nruns) {
+      int rc = launch_sgd(c, d, eta, lambda, gb, mode, 0, d->nruns);
+      if (rc) return rc;
+    }
+    if (P > 1) {
+      int rc = shift_block(c, m, item_bounds, b, nb);
+      if (rc) return rc;
+    }
+  }
+  cudaEventRecord(c->ev1, c->stream);
+  c->timed = true;
+  return MFB_OK;
+}
+
+// every rank publishes its home block (block == rank): afterwards all ranks hold all of phi/bv
+int mfb_comm_allgather_items(mfb_ctx* h, const int32_t* item_bounds) {
+  MFB_REQUIRE(h && item_bounds, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m, "communicator not initialised");
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_NCCL(g_nccl.GroupStart());
+  for (int r = 0; r < m->world; r++) {
+    const int64_t r0 = item_bounds[r], r1 = item_bounds[r + 1];
+    float* p = c->arr[MFB_PHI] + r0 * c->stride;
+    MFB_NCCL(g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * c->stride, ncclFloat, r, m->nccl, c->stream));
+    MFB_NCCL(g_nccl.Broadcast(c->arr[MFB_BV] + r0, c->arr[MFB_BV] + r0, (size_t)(r1 - r0), ncclFloat, r, m->nccl, c->stream));
+  }
+  MFB_NCCL(g_nccl.GroupEnd());
+  return MFB_OK;
+}
+
+int mfb_comm_allreduce_sse(mfb_ctx* h, double* sse, int64_t* n) {
+  MFB_REQUIRE(h && sse && n, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m, "communicator not initialised");
+  MFB_CUDA(cudaSetDevice(c->device));
+  double hb[2] = {*sse, (double)*n};
+  MFB_CUDA(cudaMemcpyAsync(m->d_red, hb, sizeof hb, cudaMemcpyHostToDevice, c->stream));
+  MFB_NCCL(g_nccl.AllReduce(m->d_red, m->d_red, 2, ncclDouble, ncclSum, m->nccl, c->stream));
+  MFB_CUDA(cudaMemcpyAsync(hb, m->d_red, sizeof hb, cudaMemcpyDeviceToHost, c->stream));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  *sse = hb[0];
+  *n = (int64_t)(hb[1] + 0.5);
+  return MFB_OK;
+}
+
+}  // extern "C"

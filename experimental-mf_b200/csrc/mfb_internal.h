@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <string>
 #include <vector>
 
@@ -56,6 +58,8 @@ struct Dataset {
   int32_t* d_last_v = nullptr;  // [nv]
   std::vector<int32_t> h_ucount, h_vcount;  // records per user / item (dpmf weights)
   double max_item_share = 0.0;              // records of the most rated item / all records
+  cudaEvent_t refreshed = nullptr;          // pending H2D refresh of the tiles (copy stream)
+  bool refresh_pending = false;
 };
 
 struct Context {
@@ -87,6 +91,7 @@ struct Context {
   int32_t* d_draws = nullptr;
   int64_t ndraws = 0;
   float* d_lams = nullptr;  // [4]
+  void* comm = nullptr;     // mfb::Comm (mfb_comm.cu): NCCL communicator of the DSGD ring
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
   int opt_row_concurrency = 8;  // bound on simultaneous updates of the hottest item row (0 = none)

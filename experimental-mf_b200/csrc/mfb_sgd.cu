@@ -323,6 +323,10 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.ld_flavour = c->opt_memopt & 3;
   a.st_flavour = (c->opt_memopt >> 2) & 3;
   a.bias_flavour = (c->opt_memopt >> 4) & 3;
+  if (d->refresh_pending) {  // tiles are being re-sent from the host (mfb_dataset_refresh_from_host)
+    MFB_CUDA(cudaStreamWaitEvent(c->stream, d->refreshed, 0));
+    d->refresh_pending = false;
+  }
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
 #define CALL(L, V) return launch_sgd_t<L, V>(c, d, a, mode)
   MFB_DISPATCH_SHAPE(a.nvec, CALL);

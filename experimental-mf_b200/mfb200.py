@@ -62,6 +62,7 @@ SIGNATURES = {
     "mfb_sgd_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "mfb_sgd_epoch_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float,
                                           C.c_float, C.c_int, C.c_int64]),
+    "mfb_dataset_refresh_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mfb_blocks_pin": (C.c_int, [C.c_void_p]),
     "mfb_blocks_unpin": (C.c_int, [C.c_void_p]),
     "mfb_sse": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -79,6 +80,13 @@ SIGNATURES = {
     "mfb_admf_set_lams": (C.c_int, [C.c_void_p, f32p]),
     "mfb_admf_get_lams": (C.c_int, [C.c_void_p, f32p]),
     "mfb_admf_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]),
+    "mfb_blocks_split_by_item": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p)]),
+    "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "mfb_comm_allgather_items": (C.c_int, [C.c_void_p, i32p]),
+    "mfb_comm_allreduce_sse": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mfb_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "mfb_launch_count": (C.c_int64, [C.c_void_p]),
 }
@@ -176,6 +184,13 @@ class Blocks:
             self.close()
         except Exception:
             pass
+
+    def split_by_item(self, bounds):
+        b = np.ascontiguousarray(bounds, np.int32)
+        n = len(b) - 1
+        out = (C.c_void_p * n)()
+        _check(lib().mfb_blocks_split_by_item(self.h, n, b.ctypes.data_as(i32p), out))
+        return [Blocks(C.c_void_p(x)) for x in out]
 
     @property
     def nblocks(self):
@@ -349,6 +364,9 @@ class Context:
     def sgd_epoch(self, ds, eta, lam, gb, mode=MODE_HOGWILD):
         _check(lib().mfb_sgd_epoch(self.h, ds, eta, lam, gb, mode))
 
+    def dataset_refresh_from_host(self, ds, blocks):
+        _check(lib().mfb_dataset_refresh_from_host(self.h, ds, blocks.h))
+
     def sgd_epoch_from_host(self, ds, blocks, eta, lam, gb, mode=MODE_HOGWILD, chunk_ratings=0):
         _check(lib().mfb_sgd_epoch_from_host(self.h, ds, blocks.h, eta, lam, gb, mode, chunk_ratings))
 
@@ -398,6 +416,25 @@ class Context:
     def admf_epoch(self, ds, eta, eta_reg, loss, gb, mode=MODE_ATOMIC):
         _check(lib().mfb_admf_epoch(self.h, ds, eta, eta_reg, loss, gb, mode))
 
+    # -- multi-GPU (DSGD ring)
+    def comm_init(self, rank, world, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().mfb_comm_init(self.h, rank, world, buf))
+
+    def dsgd_epoch(self, datasets, item_bounds, eta, lam, gb, mode=MODE_ATOMIC):
+        ds = (C.c_int * len(datasets))(*datasets)
+        b = np.ascontiguousarray(item_bounds, np.int32)
+        _check(lib().mfb_dsgd_epoch(self.h, ds, b.ctypes.data_as(i32p), eta, lam, gb, mode))
+
+    def allgather_items(self, item_bounds):
+        b = np.ascontiguousarray(item_bounds, np.int32)
+        _check(lib().mfb_comm_allgather_items(self.h, b.ctypes.data_as(i32p)))
+
+    def allreduce_sse(self, sse, n):
+        s, k = C.c_double(sse), C.c_int64(n)
+        _check(lib().mfb_comm_allreduce_sse(self.h, C.byref(s), C.byref(k)))
+        return s.value, k.value
+
     def sse(self, ds, gb):
         s, n = C.c_double(), C.c_int64()
         _check(lib().mfb_sse(self.h, ds, gb, C.byref(s), C.byref(n)))
@@ -412,6 +449,12 @@ class Context:
 
     def launch_count(self):
         return lib().mfb_launch_count(self.h)
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().mfb_comm_unique_id(buf))
+    return buf.raw
 
 
 def seteta(eta0, rnd, gam):

@@ -1,0 +1,161 @@
+"""Multi-GPU plumbing for the DSGD ring (one process per GPU).  torch.distributed is used only to
+hand the NCCL unique id around and to take max-over-ranks timings; the item-block rotation itself
+is ncclSend/ncclRecv inside libmf_b200.so (csrc/mfb_comm.cu).
+
+Partition: users are sharded over ranks in contiguous ranges, items are cut into
+`world` contiguous blocks (the generator assigns item ids through a pseudo-random permutation of
+the popularity ranks, so contiguous id ranges are balanced in expectation); rating (u, i) lives in
+cell (shard(u), block(i)).  In sub-epoch s rank p works on cell (p, (p+s) mod world).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+import mfb200 as mb
+
+
+def item_bounds(nv, world):
+    return np.array([(nv * j) // world for j in range(world + 1)], np.int32)
+
+
+def user_range(nu, rank, world):
+    return (nu * rank) // world, (nu * (rank + 1)) // world
+
+
+def dsgd_schedule(rank, world):
+    """[(block updated in sub-epoch s, send it to, receive next block from)] for one epoch."""
+    return [((rank + s) % world, (rank - 1) % world, (rank + 1) % world) for s in range(world)]
+
+
+class DsgdWorker:
+    """This rank's shard of the model and data on its GPU, plus the NCCL ring."""
+
+    def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200):
+        self.rank, self.world, self.nv = rank, world, nv
+        self.bounds = item_bounds(nv, world)
+        self.ctx = mb.Context(nu, nv, k, device)
+        self.ctx.init_normal(seed, 1e-2)  # counter-based: identical on every rank
+        self.cells = train.split_by_item(self.bounds)
+        self.cell_ds = [self.ctx.dataset_from_blocks(b) for b in self.cells]
+        self.test_ds = self.ctx.dataset_from_blocks(test)
+        self.ntrain = sum(b.nratings for b in self.cells)
+        self.ntest = test.nratings
+        self.ctx.comm_init(rank, world, unique_id)
+
+    def epoch(self, eta, lam, gb, mode=mb.MODE_ATOMIC):
+        self.ctx.dsgd_epoch(self.cell_ds, self.bounds, eta, lam, gb, mode)
+
+    def refresh_from_host(self):
+        for ds, b in zip(self.cell_ds, self.cells):
+            self.ctx.dataset_refresh_from_host(ds, b)
+
+    def global_sse(self, gb):
+        """test SSE over all ranks; needs every item block, so the home blocks are gathered first"""
+        self.ctx.allgather_items(self.bounds)
+        s, n = self.ctx.sse(self.test_ds, gb)
+        return self.ctx.allreduce_sse(s, n)
+
+    def close(self):
+        self.ctx.close()
+
+
+def bench(args, wl, shape, rank, world, local, config):
+    """bench.py --gpus N (N > 1), launched by torch.distributed.run."""
+    import torch
+    import torch.distributed as dist
+    from bench import ETA0, GAM, GB, LAMBDA, METRIC, UNIT, ClockSampler, bytes_per_update, measured_peak
+    nu, nv, nnz, k, test_frac = shape
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(mb.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    unique_id = bytes(uid.cpu().numpy().tobytes())
+
+    u0, u1 = user_range(nu, rank, world)
+    t0 = time.time()
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=test_frac, user_begin=u0, user_end=u1))
+    gen_s = time.time() - t0
+    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, unique_id)
+    stream = torch.cuda.current_stream()
+    w.ctx.set_stream(stream.cuda_stream)
+    mode = {"hogwild": mb.MODE_HOGWILD, "atomic": mb.MODE_ATOMIC}[args.schedule]
+    launches0 = w.ctx.launch_count()
+    epoch = [0]
+
+    def step():
+        epoch[0] += 1
+        w.epoch(mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mode)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([max(ev0.elapsed_time(ev1), 0.0), 1e3 * (time.perf_counter() - t0)], device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(ms[0]), float(ms[1])
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, _ = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    ntrain = int(tot[0])
+    value = ntrain * args.steps / (total_ms * 1e-3)
+
+    # end to end: every step re-sends this rank's rating tiles from pinned host memory and reads
+    # the global test SSE back
+    for b in w.cells:
+        b.pin()
+    sse_host = []
+
+    def step_e2e():
+        epoch[0] += 1
+        w.refresh_from_host()
+        w.epoch(mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mode)
+        sse_host.append(w.global_sse(GB))
+
+    step_e2e()
+    e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps)
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms)
+    h2d = sum(b.nratings * 8 + b.nruns * 8 + 4 for b in w.cells)
+    h2d_t = torch.tensor([h2d], dtype=torch.int64, device="cuda")
+    dist.all_reduce(h2d_t)
+    sse, n = sse_host[-1]
+    launches = w.ctx.launch_count() - launches0
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = value * bytes_per_update(k) / 1e9 / world  # per GPU
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU, whole DSGD epoch (P cell kernels + P ring shifts), algorithmic bytes"},
+            "cpu_baseline": None,
+            "e2e": {"value": ntrain * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d_t[0]), "d2h_bytes_per_step": 16 * world,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "what": "per rank: H2D of its cell tiles + mfb_dsgd_epoch + gathered test SSE, max over ranks"},
+            "clocks": clocks, "gpu_launches": launches, "test_rmse": float(np.sqrt(sse / max(n, 1))),
+            "epochs_run": epoch[0], "train_ratings": ntrain, "gen_s": round(gen_s, 2),
+            "dsgd": {"cells_per_rank": world, "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
+                     "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch"},
+        }
+        print(json.dumps(line))
+    w.close()
+    dist.destroy_process_group()

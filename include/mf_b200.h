@@ -165,6 +165,9 @@ int mfb_sgd_epoch(mfb_ctx* ctx, int ds, float eta, float lambda, float gb, int m
  * finalized dataset created from the same blocks; its HBM tiles are the copy target. */
 int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float eta, float lambda,
                             float gb, int mode, int64_t chunk_ratings);
+/* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
+ * the next epoch kernel on `ds` waits for the copy.  Used by the multi-GPU end-to-end path. */
+int mfb_dataset_refresh_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src);
 int mfb_blocks_pin(mfb_blocks* b);
 int mfb_blocks_unpin(mfb_blocks* b);
 /* MF::calc_mse (model.cc:41-73): SUM of squared errors and the record count. */
@@ -213,6 +216,25 @@ int mfb_admf_get_lams(mfb_ctx* ctx, float lams[4]);
  * (model.h:86-102); eta_reg = AdaptRegMF::set_etareg's value (model.cc:386-388);
  * mode ORDERED (serial, exact lambda trajectory) or ATOMIC (parallel) */
 int mfb_admf_epoch(mfb_ctx* ctx, int ds, float eta, float eta_reg, int loss, float gb, int mode);
+
+/* ---- multi-GPU: DSGD stratification (new design; the reference is single-process) -------------
+ * One process per GPU.  Users are sharded over ranks, items are cut into `world` blocks by
+ * item_bounds[world+1]; datasets[j] holds this rank's ratings whose item is in block j (see
+ * mfb_blocks_split_by_item).  mfb_dsgd_epoch runs `world` sub-epochs; after each one the item
+ * block just updated is passed to rank-1 and the next one received from rank+1 with
+ * ncclSend/ncclRecv on a dedicated stream.  At entry and exit rank r holds block r.
+ * The unique id is created on rank 0 and distributed by the host program (bench.py uses
+ * torch.distributed for that plumbing). */
+int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bounds, mfb_blocks** out);
+int mfb_comm_unique_id(void* out128);
+int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
+int mfb_comm_destroy(mfb_ctx* ctx);
+int mfb_dsgd_epoch(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
+                   float gb, int mode);
+/* make all of phi/bv valid on every rank (each rank publishes its home block) - before evaluation */
+int mfb_comm_allgather_items(mfb_ctx* ctx, const int32_t* item_bounds);
+/* sum (sse, n) over the ranks */
+int mfb_comm_allreduce_sse(mfb_ctx* ctx, double* sse, int64_t* n);
 
 /* device time in ms of the most recent epoch / sse call's kernels (CUDA events on the
  * context's stream; valid after mfb_sync) and the number of kernel launches since create */

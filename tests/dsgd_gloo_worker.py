@@ -1,0 +1,57 @@
+"""Worker of tests/test_dsgd_host.py: one emulated DSGD rank on the CPU (gloo).  The cell update is
+the CPU oracle; everything else - user sharding through the generator, the item split, the
+schedule and the ring exchange order - is the product's host logic."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "experimental-mf_b200"))
+import mfb200 as mb  # noqa: E402
+import mfb_dsgd  # noqa: E402
+import oraclelib as ol  # noqa: E402
+
+NU, NV, NNZ, DIM, GB, EPOCHS = 400, 150, 20000, 16, 2.76, 2
+
+
+def cell_datasets(rank, world):
+    u0, u1 = mfb_dsgd.user_range(NU, rank, world)
+    tr, _, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.0, users_per_block=40, user_begin=u0, user_end=u1))
+    bounds = mfb_dsgd.item_bounds(NV, world)
+    return [ol.Dataset(b.block_off, b.run_uid, b.run_off, b.vid, b.rating) for b in tr.split_by_item(bounds)], bounds
+
+
+def main():
+    out = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cells, bounds = cell_datasets(rank, world)
+    m = ol.Model(NU, NV, DIM, seed=3)  # same seeded start on every rank
+    mm = m.as_mfo()
+    for ep in range(1, EPOCHS + 1):
+        eta = mb.seteta(2e-2, ep, 1.0)
+        for b, to, frm in mfb_dsgd.dsgd_schedule(rank, world):
+            dd = cells[b].as_mfo()
+            ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), eta, 5e-3, GB)
+            nb = (b + 1) % world
+            send = torch.from_numpy(np.ascontiguousarray(np.c_[m.phi[bounds[b]:bounds[b + 1]], m.bv[bounds[b]:bounds[b + 1]]]))
+            recv = torch.empty((bounds[nb + 1] - bounds[nb], m.stride + 1), dtype=torch.float32)
+            reqs = [dist.isend(send, to), dist.irecv(recv, frm)]
+            for r in reqs:
+                r.wait()
+            m.phi[bounds[nb]:bounds[nb + 1]] = recv[:, :m.stride].numpy()
+            m.bv[bounds[nb]:bounds[nb + 1]] = recv[:, m.stride].numpy()
+    u0, u1 = mfb_dsgd.user_range(NU, rank, world)
+    np.savez(os.path.join(out, "rank%d.npz" % rank), theta=m.theta[u0:u1], bu=m.bu[u0:u1],
+             phi=m.phi[bounds[rank]:bounds[rank + 1]], bv=m.bv[bounds[rank]:bounds[rank + 1]])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,11 +169,12 @@ class Dataset:
     """A rating file in file order (blocks -> user-runs -> records), as numpy arrays."""
 
     def __init__(self, block_off, run_uid, run_off, vid, rating):
-        self.block_off = np.ascontiguousarray(block_off, dtype=np.int64)
-        self.run_uid = np.ascontiguousarray(run_uid, dtype=np.int32)
-        self.run_off = np.ascontiguousarray(run_off, dtype=np.int64)
-        self.vid = np.ascontiguousarray(vid, dtype=np.int32)
-        self.rating = np.ascontiguousarray(rating, dtype=np.float32)
+        # always own the memory: the inputs may be views into an mfb_blocks that is freed later
+        self.block_off = np.array(block_off, dtype=np.int64, order="C", copy=True)
+        self.run_uid = np.array(run_uid, dtype=np.int32, order="C", copy=True)
+        self.run_off = np.array(run_off, dtype=np.int64, order="C", copy=True)
+        self.vid = np.array(vid, dtype=np.int32, order="C", copy=True)
+        self.rating = np.array(rating, dtype=np.float32, order="C", copy=True)
 
     @property
     def nratings(self):

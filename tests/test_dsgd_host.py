@@ -1,0 +1,78 @@
+"""Host logic of the multi-GPU DSGD path on the CPU (no GPU needed): the cell schedule, the item
+split, user sharding, and a 2-process gloo ring that must reproduce a single-process walk of the
+same cell schedule."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+import mfb200 as mb
+import mfb_dsgd
+import oraclelib as ol
+
+
+def test_schedule_is_a_ring_latin_square():
+    for P in range(1, 9):
+        sched = [mfb_dsgd.dsgd_schedule(r, P) for r in range(P)]
+        for s in range(P):
+            assert sorted(sched[r][s][0] for r in range(P)) == list(range(P))  # disjoint item blocks
+        for r in range(P):
+            assert sorted(x[0] for x in sched[r]) == list(range(P))  # every block once per epoch
+            assert sched[r][0][0] == r  # epochs start (and end) with block r at rank r
+            for s in range(P):
+                b, to, frm = sched[r][s]
+                assert to == (r - 1) % P and frm == (r + 1) % P
+                # what I work on next is what my ring successor just finished
+                assert sched[r][(s + 1) % P][0] == sched[frm][s][0]
+
+
+def test_split_by_item_partitions_every_record():
+    nu, nv = 500, 130
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 30000, test_frac=0.0, users_per_block=60))
+    bounds = mfb_dsgd.item_bounds(nv, 4)
+    parts = tr.split_by_item(bounds)
+    assert sum(p.nratings for p in parts) == tr.nratings
+    keys = []
+    for j, p in enumerate(parts):
+        assert p.nblocks == tr.nblocks
+        if p.nratings:
+            assert p.vid.min() >= bounds[j] and p.vid.max() < bounds[j + 1]
+        assert (np.diff(p.run_off) > 0).all()  # empty runs are dropped
+        u = np.repeat(p.run_uid, np.diff(p.run_off)).astype(np.int64)
+        keys.append(u * nv + p.vid)
+    uall = np.repeat(tr.run_uid, np.diff(tr.run_off)).astype(np.int64)
+    assert sorted(np.concatenate(keys).tolist()) == sorted((uall * nv + tr.vid).tolist())
+    # relative order of a user's records inside a part is the file order
+    p0 = parts[0]
+    m = (tr.vid >= bounds[0]) & (tr.vid < bounds[1])
+    np.testing.assert_array_equal(p0.vid, tr.vid[m])
+    np.testing.assert_array_equal(p0.rating, tr.rating[m])
+
+
+def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib):
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29631",
+                    os.path.join(here, "dsgd_gloo_worker.py"), str(tmp_path)], check=True, env=env, timeout=300)
+    import dsgd_gloo_worker as w
+    world = 2
+    m = ol.Model(w.NU, w.NV, w.DIM, seed=3)
+    mm = m.as_mfo()
+    cells = [w.cell_datasets(r, world)[0] for r in range(world)]
+    for ep in range(1, w.EPOCHS + 1):
+        eta = mb.seteta(2e-2, ep, 1.0)
+        for s in range(world):  # cells of one sub-epoch share no user and no item: any order
+            for r in range(world):
+                dd = cells[r][mfb_dsgd.dsgd_schedule(r, world)[s][0]].as_mfo()
+                oracle_lib.mfo_sgd_epoch(C.byref(mm), C.byref(dd), eta, 5e-3, w.GB)
+    bounds = mfb_dsgd.item_bounds(w.NV, world)
+    for r in range(world):
+        got = np.load(tmp_path / ("rank%d.npz" % r))
+        u0, u1 = mfb_dsgd.user_range(w.NU, r, world)
+        np.testing.assert_array_equal(got["theta"], m.theta[u0:u1])
+        np.testing.assert_array_equal(got["bu"], m.bu[u0:u1])
+        np.testing.assert_array_equal(got["phi"], m.phi[bounds[r]:bounds[r + 1]])  # block r is home again
+        np.testing.assert_array_equal(got["bv"], m.bv[bounds[r]:bounds[r + 1]])

@@ -1,0 +1,60 @@
+"""DSGD path pieces that can be checked on ONE GPU: world-size-1 ring, and the stratified cell
+datasets walked in schedule order (what P GPUs execute, serialised) against the CPU oracle walking
+the same schedule.  The real multi-rank run is tools/dsgd_check.py (torchrun, >= 2 GPUs)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mfb200 as mb
+import mfb_dsgd
+import oraclelib as ol
+from gpu_common import ctx_from_model, model_equal, oracle_sgd
+
+pytestmark = pytest.mark.gpu
+GB = 2.76
+
+
+def test_world_size_one_ring_equals_plain_epoch():
+    nu, nv, dim = 500, 200, 64
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, 30000, test_frac=0.1, users_per_block=50))
+    m = ol.Model(nu, nv, dim, seed=1)
+    th, ph = m.dense()
+    w = mfb_dsgd.DsgdWorker(nu, nv, dim, 0, 1, 0, tr, te, mb.comm_unique_id())
+    w.ctx.set_factors(th, ph, m.bu, m.bv)
+    c = ctx_from_model(m)
+    d = c.dataset_from_blocks(tr)
+    for ep in (1, 2):
+        w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
+        c.sgd_epoch(d, mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
+    for a, b in zip(w.ctx.get_factors(), c.get_factors()):
+        np.testing.assert_array_equal(a, b)
+    s, n = w.global_sse(GB)
+    s2, n2 = c.sse(c.dataset_from_blocks(te), GB)
+    assert n == n2 and abs(s - s2) <= 1e-9 * s2
+    w.close()
+    c.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cell_schedule_on_one_gpu_equals_oracle_schedule(world):
+    nu, nv, dim = 600, 240, 32
+    m = ol.Model(nu, nv, dim, seed=2)
+    c = ctx_from_model(m)
+    bounds = mfb_dsgd.item_bounds(nv, world)
+    cells_gpu, cells_cpu = [], []
+    for r in range(world):
+        u0, u1 = mfb_dsgd.user_range(nu, r, world)
+        tr, _, _ = mb.generate(mb.gen_params(nu, nv, 40000, test_frac=0.0, users_per_block=50, user_begin=u0, user_end=u1))
+        parts = tr.split_by_item(bounds)
+        cells_gpu.append([c.dataset_from_blocks(p) for p in parts])
+        cells_cpu.append([ol.Dataset(p.block_off, p.run_uid, p.run_off, p.vid, p.rating) for p in parts])
+    for ep in (1, 2):
+        eta = mb.seteta(2e-2, ep, 1.0)
+        for s in range(world):
+            for r in range(world):
+                b = mfb_dsgd.dsgd_schedule(r, world)[s][0]
+                c.sgd_epoch(cells_gpu[r][b], eta, 5e-3, GB, mb.MODE_ORDERED)
+                oracle_sgd(m, cells_cpu[r][b], eta, 5e-3, GB)
+    assert model_equal(c, m)
+    c.close()

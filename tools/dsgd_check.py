@@ -1,0 +1,84 @@
+"""Multi-rank check of the DSGD ring on >= 2 GPUs (run under torchrun via gpurun --gpus N):
+ordered cells + NCCL ring shifts must equal the CPU oracle walking the same cell schedule, bit for
+bit; then the parallel schedule's test RMSE is compared with a single-GPU run."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "experimental-mf_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mfb200 as mb  # noqa: E402
+import mfb_dsgd  # noqa: E402
+import oraclelib as ol  # noqa: E402
+
+NU, NV, NNZ, DIM, GB = 6040, 3706, 1_000_000, 32, 2.76
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid.copy_(torch.frombuffer(bytearray(mb.comm_unique_id()), dtype=torch.uint8))
+dist.broadcast(uid, 0)
+unique_id = bytes(uid.cpu().numpy().tobytes())
+u0, u1 = mfb_dsgd.user_range(NU, rank, world)
+tr, te, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=u0, user_end=u1))
+m = ol.Model(NU, NV, DIM, seed=11)
+th, ph = m.dense()
+w = mfb_dsgd.DsgdWorker(NU, NV, DIM, rank, world, local, tr, te, unique_id)
+w.ctx.set_factors(th, ph, m.bu, m.bv)
+for ep in (1, 2):
+    w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
+w.ctx.allgather_items(w.bounds)
+theta, phi, bu, bv = w.ctx.get_factors()
+mine = torch.from_numpy(np.ascontiguousarray(theta)).cuda()
+allth = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(allth, mine)
+ok = True
+if rank == 0:
+    # the oracle walks the same cell schedule (cells of one sub-epoch are disjoint)
+    cells = []
+    for r in range(world):
+        a, b = mfb_dsgd.user_range(NU, r, world)
+        t, _, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=a, user_end=b))
+        cells.append([ol.Dataset(p.block_off, p.run_uid, p.run_off, p.vid, p.rating) for p in t.split_by_item(w.bounds)])
+    mm = m.as_mfo()
+    for ep in (1, 2):
+        for s in range(world):
+            for r in range(world):
+                dd = cells[r][mfb_dsgd.dsgd_schedule(r, world)[s][0]].as_mfo()
+                ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
+    ok &= np.array_equal(phi, m.phi[:, :DIM]) and np.array_equal(bv, m.bv)
+    for r in range(world):
+        a, b = mfb_dsgd.user_range(NU, r, world)
+        ok &= np.array_equal(allth[r].cpu().numpy()[a:b], m.theta[a:b, :DIM])
+    print("DSGD ordered, %d ranks: bit-exact vs oracle schedule walk: %s" % (world, ok), flush=True)
+# parallel schedule: RMSE after 10 epochs vs the serial oracle
+w.ctx.set_factors(th, ph, m.bu, m.bv)
+traj = []
+for ep in range(1, 11):
+    w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ATOMIC)
+    s, n = w.global_sse(GB)
+    traj.append(float(np.sqrt(s / n)))
+if rank == 0:
+    print("DSGD atomic tRMSE", " ".join("%.4f" % x for x in traj), flush=True)
+    m2 = ol.Model(NU, NV, DIM, seed=11)
+    t_all, te_all, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1))
+    dtr = ol.Dataset(t_all.block_off, t_all.run_uid, t_all.run_off, t_all.vid, t_all.rating)
+    dte = ol.Dataset(te_all.block_off, te_all.run_uid, te_all.run_off, te_all.vid, te_all.rating)
+    mm, dd, tt = m2.as_mfo(), dtr.as_mfo(), dte.as_mfo()
+    want = []
+    for ep in range(1, 11):
+        ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
+        n = C.c_int64()
+        s = ol.oracle().mfo_sse(C.byref(mm), C.byref(tt), GB, C.byref(n))
+        want.append(float(np.sqrt(s / n.value)))
+    print("serial oracle tRMSE", " ".join("%.4f" % x for x in want), flush=True)
+    print("final |d rmse| = %.5f" % abs(traj[-1] - want[-1]), flush=True)
+w.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
