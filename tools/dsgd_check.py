@@ -29,6 +29,7 @@ u0, u1 = mfb_dsgd.user_range(NU, rank, world)
 tr, te, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=u0, user_end=u1))
 m = ol.Model(NU, NV, DIM, seed=11)
 th, ph = m.dense()
+bu0, bv0 = m.bu.copy(), m.bv.copy()  # rank 0 trains `m` in place below
 w = mfb_dsgd.DsgdWorker(NU, NV, DIM, rank, world, local, tr, te, unique_id)
 w.ctx.set_factors(th, ph, m.bu, m.bv)
 for ep in (1, 2):
@@ -58,7 +59,7 @@ if rank == 0:
         ok &= np.array_equal(allth[r].cpu().numpy()[a:b], m.theta[a:b, :DIM])
     print("DSGD ordered, %d ranks: bit-exact vs oracle schedule walk: %s" % (world, ok), flush=True)
 # parallel schedule: RMSE after 10 epochs vs the serial oracle
-w.ctx.set_factors(th, ph, m.bu, m.bv)
+w.ctx.set_factors(th, ph, bu0, bv0)
 traj = []
 for ep in range(1, 11):
     w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ATOMIC)
