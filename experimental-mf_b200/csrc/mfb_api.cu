@@ -252,6 +252,9 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "max_groups")) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
+  } else if (!strcmp(name, "kernel")) {
+    MFB_REQUIRE(value == 1 || value == 2, "kernel must be 1 or 2");
+    c->opt_kernel = value;
   } else if (!strcmp(name, "memopt")) {
     c->opt_memopt = value;
   } else {

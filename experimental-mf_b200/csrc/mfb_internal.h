@@ -94,6 +94,7 @@ struct Context {
   void* comm = nullptr;     // mfb::Comm (mfb_comm.cu): NCCL communicator of the DSGD ring
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
+  int opt_kernel = 2;           // 1 = one record at a time, 2 = batched (4 records) where available
   int opt_row_concurrency = 8;  // bound on simultaneous updates of the hottest item row (0 = none)
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
