@@ -44,14 +44,28 @@ static int alloc_array(Context* c, int which) {
   if (c->arr[which]) return MFB_OK;
   size_t n = (size_t)array_rows(c, which) * array_stride(c, which);
   if (which == MFB_LAMBDA_U || which == MFB_LAMBDA_V) n = (size_t)c->stride;  // padded with zeros
-  if (n == 0) n = 1;
+  n = (n + 15) / 16 * 16;  // kernels fetch the aligned 16 bytes around a bias element
+  if (n == 0) n = 16;
   MFB_CUDA(cudaMalloc(&c->arr[which], n * sizeof(float)));
   MFB_CUDA(cudaMemsetAsync(c->arr[which], 0, n * sizeof(float), c->stream));
   return MFB_OK;
 }
 
+int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
+                       int inflight, float eta) {
+  if (c->opt_max_groups > 0) return std::min<int64_t>(groups, c->opt_max_groups);
+  if (c->opt_row_concurrency > 0 && max_item_share > 0.0) {
+    double budget = (double)c->opt_row_concurrency;
+    if (c->opt_eta_scaling && eta > 0.f) budget *= 0.02 / (double)eta;
+    groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(budget / (max_item_share * std::max(inflight, 1)))));
+  }
+  if (c->opt_run_fraction_ppm > 0 && total_runs > 0)
+    groups = std::min<int64_t>(groups, std::max<int64_t>(1, total_runs * c->opt_run_fraction_ppm / 1000000));
+  return groups;
+}
+
 LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
-                        double max_item_share, int64_t total_runs) {
+                        double max_item_share, int64_t total_runs, int inflight, float eta) {
   int max_threads = c->opt_threads;
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, max_threads, 0);
@@ -60,14 +74,7 @@ LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_
   const int groups_per_warp = 32 / lpr;
   int64_t groups = (int64_t)c->sm_count * per_sm * (max_threads / 32) * groups_per_warp;  // hardware
   groups = std::min(groups, std::max<int64_t>(groups_needed, 1));
-  if (c->opt_max_groups > 0) {
-    groups = std::min<int64_t>(groups, c->opt_max_groups);
-  } else {
-    if (c->opt_row_concurrency > 0 && max_item_share > 0.0)
-      groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(c->opt_row_concurrency / max_item_share)));
-    if (c->opt_run_fraction_ppm > 0 && total_runs > 0)
-      groups = std::min<int64_t>(groups, std::max<int64_t>(1, total_runs * c->opt_run_fraction_ppm / 1000000));
-  }
+  groups = bounded_groups(c, groups, max_item_share, total_runs, inflight, eta);
   // spread the warps over all SMs: one CTA per SM with as many warps as needed, more CTAs beyond 8
   const int64_t warps = (groups + groups_per_warp - 1) / groups_per_warp;
   LaunchShape ls;
@@ -81,6 +88,8 @@ LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_
     ls.threads = 32 * ((warps_per_sm + ctas - 1) / ctas);
     ls.grid = c->sm_count * ctas;
   }
+  c->last_grid = ls.grid;
+  c->last_threads = ls.threads;
   return ls;
 }
 
@@ -253,8 +262,13 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
   } else if (!strcmp(name, "kernel")) {
-    MFB_REQUIRE(value == 1 || value == 2, "kernel must be 1 or 2");
+    MFB_REQUIRE(value >= 1 && value <= 3, "kernel must be 1, 2 or 3");
     c->opt_kernel = value;
+  } else if (!strcmp(name, "ring")) {
+    MFB_REQUIRE(value >= 1 && value <= 4, "ring must be 1..4");
+    c->opt_ring = value;
+  } else if (!strcmp(name, "eta_scaling")) {
+    c->opt_eta_scaling = value != 0;
   } else if (!strcmp(name, "memopt")) {
     c->opt_memopt = value;
   } else {

@@ -94,8 +94,13 @@ struct Context {
   void* comm = nullptr;     // mfb::Comm (mfb_comm.cu): NCCL communicator of the DSGD ring
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
-  int opt_kernel = 2;           // 1 = one record at a time, 2 = batched (4 records) where available
-  int opt_row_concurrency = 8;  // bound on simultaneous updates of the hottest item row (0 = none)
+  int opt_kernel = 3;           // SGD kernel: 3 = sub-warp streaming (mfb_sgd_stream.cu); 1 = warp per run,
+                                // one record at a time; 2 = warp per run, 4 records batched
+  int opt_ring = 3;             // streaming kernel: item rows in flight per sub-warp (1, 2, 3, 4)
+  int opt_row_concurrency = 48; // bound on the stale updates of the hottest item row in flight at once,
+                                // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t
+  int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
+  int last_grid = 0, last_threads = 0;  // launch shape of the most recent epoch kernel
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
   std::vector<Dataset> datasets;
@@ -105,20 +110,24 @@ int64_t array_rows(const Context* c, int which);
 int array_cols(const Context* c, int which);      // logical columns (dim or 1)
 int array_stride(const Context* c, int which);    // device row stride in floats
 
-// How many sub-warps may work at once.  Every sub-warp is, at any instant, updating one item row;
-// the hottest item (share p of all records) is therefore being updated by about W*p of them.
-// The reference runs at most --fly (default 8) SgdFilter calls at a time (main.cc:50,97); the
-// same bound is kept PER ROW here: W <= row_concurrency / p.  Without it thousands of sub-warps
-// read the same stale row: plain stores lose all but one update (measured: no convergence at ML-1M
-// shape) and atomic accumulation applies them all at once (measured: divergence).
+// How many sub-warps may work at once.  Every sub-warp holds `inflight` item rows between gather
+// and write-back; the hottest item (share p of all records) is therefore hit by about
+// W*inflight*p stale updates at once, each applied with step eta.  The reference runs at most
+// --fly (default 8) SgdFilter calls at a time (main.cc:50,97); here the bound is on the product
+//     eta * W * inflight * p  <=  0.02 * row_concurrency
+// (0.02 = the reference's default eta, main.cc:97).  Without it thousands of sub-warps read the
+// same stale row: plain stores lose all but one update (measured: no convergence at ML-1M shape)
+// and atomic accumulation applies them all at once (measured: divergence between 1.3 and 1.8).
 // Second bound: the user-runs in flight are a "mini-batch" whose members do not see each other's
 // updates; measured test-RMSE error vs the serial oracle grows with W / (runs in the file)
 // (0.09% -> 7e-5, 0.35% -> 2.6e-4, 0.7% -> 9e-4, 1.4% -> 3e-3), so W <= run_fraction * runs.
 struct LaunchShape {
   int grid, threads;
 };
+int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
+                       int inflight, float eta);
 LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
-                        double max_item_share, int64_t total_runs);
+                        double max_item_share, int64_t total_runs, int inflight = 6, float eta = 0.f);
 
 // kernels (mfb_sgd.cu)
 // runs [run_begin, run_end) of the dataset, in the given schedule

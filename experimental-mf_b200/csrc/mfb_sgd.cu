@@ -16,23 +16,10 @@
 #include "mfb_group.cuh"
 #include "mfb_internal.h"
 #include "mfb_philox.cuh"
+#include "mfb_sgd_args.cuh"
 
 namespace mfb {
 
-struct SgdArgs {
-  float* theta;
-  float* phi;
-  float* bu;
-  float* bv;
-  const int32_t* run_uid;
-  const int32_t* run_off;
-  const int32_t* vid;
-  const float* rating;
-  int* counter;
-  int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
-  float eta, lameta, lm1, gb;
-  int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
-};
 
 // One rating, fast arithmetic (fused multiply-adds, butterfly dot).
 template <int LPR, int VPL, int MODE>
@@ -413,10 +400,12 @@ int launch_sgd_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
     constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
     const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>
                                             : (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
-    if (LPR == 32 && VPL == 1 && c->opt_kernel == 2)
+    if (LPR == 32 && VPL == 1 && c->opt_kernel == 2)  // b4 (below)
       k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel_b4<MFB_MODE_ATOMIC>
                                   : (const void*)sgd_epoch_kernel_b4<MFB_MODE_HOGWILD>;
-    const LaunchShape ls = pick_launch(c, k, LPR, a.nruns - a.run_begin, d->max_item_share, d->nruns);
+    const bool b4 = LPR == 32 && VPL == 1 && c->opt_kernel == 2;
+    const LaunchShape ls = pick_launch(c, k, LPR, a.nruns - a.run_begin, d->max_item_share, d->nruns,
+                                       b4 ? 8 : B, a.eta);
     void* args[] = {(void*)&a};
     MFB_CUDA(cudaLaunchKernel(k, dim3(ls.grid), dim3(ls.threads), args, 0, c->stream));
   }
@@ -428,7 +417,7 @@ int launch_sgd_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
 template <int LPR, int VPL>
 int launch_sse_t(Context* c, const SseArgs& a) {
   auto k = sse_kernel<LPR, VPL>;
-  const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, 0.0, 0);  // read-only: no bound
+  const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, 0.0, 0, 1, 0.f);  // read-only: no bound
   k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   MFB_CUDA(cudaGetLastError());
   c->launches++;
@@ -478,6 +467,11 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
     d->refresh_pending = false;
   }
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+  if (mode != MFB_MODE_ORDERED && c->opt_kernel == 3) {
+    bool handled = false;
+    const int rc = launch_sgd_stream(c, d, a, mode, &handled);
+    if (rc != MFB_OK || handled) return rc;
+  }
 #define CALL(L, V) return launch_sgd_t<L, V>(c, d, a, mode)
   MFB_DISPATCH_SHAPE(a.nvec, CALL);
 #undef CALL

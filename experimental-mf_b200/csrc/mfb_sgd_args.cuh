@@ -1,0 +1,31 @@
+// Kernel arguments of the plain-SGD epoch kernels (mfb_sgd.cu, mfb_sgd_stream.cu).
+#ifndef MFB_SGD_ARGS_CUH
+#define MFB_SGD_ARGS_CUH
+
+#include <stdint.h>
+
+namespace mfb {
+
+struct SgdArgs {
+  float* theta;
+  float* phi;
+  float* bu;
+  float* bv;
+  const int32_t* run_uid;
+  const int32_t* run_off;
+  const int32_t* vid;
+  const float* rating;
+  int* counter;
+  int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
+  float eta, lameta, lm1, gb;
+  int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
+};
+
+struct Context;
+struct Dataset;
+// mfb_sgd_stream.cu: the sub-warp streaming kernel (production schedule); returns MFB_OK or an
+// error; `handled` is false when the row shape has no streaming instantiation
+int launch_sgd_stream(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled);
+
+}  // namespace mfb
+#endif
