@@ -52,15 +52,18 @@ static int alloc_array(Context* c, int which) {
 }
 
 int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
-                       int inflight, float eta) {
+                       double inflight, float eta) {
   if (c->opt_max_groups > 0) return std::min<int64_t>(groups, c->opt_max_groups);
+  // both budgets are on (step size) x (stale updates applied at once): they widen as eta decays
+  const double widen = (c->opt_eta_scaling && eta > 0.f) ? 0.02 / (double)eta : 1.0;
   if (c->opt_row_concurrency > 0 && max_item_share > 0.0) {
-    double budget = (double)c->opt_row_concurrency;
-    if (c->opt_eta_scaling && eta > 0.f) budget *= 0.02 / (double)eta;
-    groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(budget / (max_item_share * std::max(inflight, 1)))));
+    const double budget = (double)c->opt_row_concurrency * widen;
+    groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(budget / (max_item_share * std::max(inflight, 0.1)))));
   }
-  if (c->opt_run_fraction_ppm > 0 && total_runs > 0)
-    groups = std::min<int64_t>(groups, std::max<int64_t>(1, total_runs * c->opt_run_fraction_ppm / 1000000));
+  if (c->opt_run_fraction_ppm > 0 && total_runs > 0) {
+    const double frac = (double)c->opt_run_fraction_ppm * 1e-6 * (c->opt_eta_scaling >= 2 ? widen : 1.0);
+    groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(total_runs * frac)));
+  }
   return groups;
 }
 
@@ -218,6 +221,7 @@ void mfb_destroy(mfb_ctx* h) {
   cudaFree(c->d_norms);
   cudaFree(c->d_val_u); cudaFree(c->d_val_v); cudaFree(c->d_val_r);
   cudaFree(c->d_draws); cudaFree(c->d_lams);
+  cudaFree(c->d_version); cudaFree(c->d_probe);
   cudaFreeHost(c->h_accum);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -262,13 +266,16 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
   } else if (!strcmp(name, "kernel")) {
-    MFB_REQUIRE(value >= 1 && value <= 3, "kernel must be 1, 2 or 3");
+    MFB_REQUIRE(value >= 0 && value <= 3, "kernel must be 0 (choose), 1, 2 or 3");
     c->opt_kernel = value;
   } else if (!strcmp(name, "ring")) {
-    MFB_REQUIRE(value >= 1 && value <= 4, "ring must be 1..4");
+    MFB_REQUIRE(value >= 0 && value <= 4, "ring must be 0..4");
     c->opt_ring = value;
+  } else if (!strcmp(name, "throttle")) {
+    c->opt_throttle = value != 0;
   } else if (!strcmp(name, "eta_scaling")) {
-    c->opt_eta_scaling = value != 0;
+    MFB_REQUIRE(value >= 0 && value <= 2, "eta_scaling must be 0, 1 (row budget) or 2 (row and run budgets)");
+    c->opt_eta_scaling = value;
   } else if (!strcmp(name, "memopt")) {
     c->opt_memopt = value;
   } else {
@@ -846,6 +853,43 @@ int mfb_admf_epoch(mfb_ctx* h, int ds, float eta, float eta_reg, int loss, float
   return rc;
 }
 
+// Staleness probe: item >= 0 arms it (per-item update counters, zeroed), item < 0 disarms it.
+int mfb_probe_arm(mfb_ctx* h, int item) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  if (item < 0) {
+    cudaFree(c->d_version);
+    cudaFree(c->d_probe);
+    c->d_version = nullptr;
+    c->d_probe = nullptr;
+    return MFB_OK;
+  }
+  MFB_REQUIRE(item < c->nv, "probe item out of range");
+  if (!c->d_version) {
+    MFB_CUDA(cudaMalloc(&c->d_version, (size_t)c->nv * sizeof(int)));
+    MFB_CUDA(cudaMalloc(&c->d_probe, 4 * sizeof(unsigned long long)));
+  }
+  MFB_CUDA(cudaMemset(c->d_version, 0, (size_t)c->nv * sizeof(int)));
+  MFB_CUDA(cudaMemset(c->d_probe, 0, 4 * sizeof(unsigned long long)));
+  c->probe_item = item;
+  return MFB_OK;
+}
+
+// out[0..3] = {stale updates summed over all updates, updates, the same two for the probed item};
+// counters restart from zero
+int mfb_probe_read(mfb_ctx* h, uint64_t out[4]) {
+  MFB_REQUIRE(h && out, "NULL argument");
+  Context* c = &h->c;
+  MFB_REQUIRE(c->d_probe, "probe not armed");
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  MFB_CUDA(cudaMemcpy(out, c->d_probe, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  MFB_CUDA(cudaMemset(c->d_probe, 0, 4 * sizeof(unsigned long long)));
+  return MFB_OK;
+}
+
 float mfb_last_kernel_ms(mfb_ctx* h) {
   if (!h || !h->c.timed) return -1.f;
   float ms = -1.f;
@@ -855,5 +899,14 @@ float mfb_last_kernel_ms(mfb_ctx* h) {
 }
 
 int64_t mfb_launch_count(mfb_ctx* h) { return h ? h->c.launches : 0; }
+
+int mfb_last_launch(mfb_ctx* h, int out[4]) {
+  MFB_REQUIRE(h && out, "NULL argument");
+  out[0] = h->c.use_kernel;
+  out[1] = h->c.last_grid;
+  out[2] = h->c.last_threads;
+  out[3] = h->c.last_ring;
+  return MFB_OK;
+}
 
 }  // extern "C"

@@ -91,16 +91,22 @@ struct Context {
   int32_t* d_draws = nullptr;
   int64_t ndraws = 0;
   float* d_lams = nullptr;  // [4]
+  int* d_version = nullptr;                 // staleness probe (mfb_probe_*): per-item update counters
+  unsigned long long* d_probe = nullptr;    // [4]
+  int probe_item = -1;
   void* comm = nullptr;     // mfb::Comm (mfb_comm.cu): NCCL communicator of the DSGD ring
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
-  int opt_kernel = 3;           // SGD kernel: 3 = sub-warp streaming (mfb_sgd_stream.cu); 1 = warp per run,
-                                // one record at a time; 2 = warp per run, 4 records batched
-  int opt_ring = 3;             // streaming kernel: item rows in flight per sub-warp (1, 2, 3, 4)
-  int opt_row_concurrency = 48; // bound on the stale updates of the hottest item row in flight at once,
+  int opt_kernel = 0;           // SGD kernel: 3 = sub-warp streaming (mfb_sgd_stream.cu); 1 = warp per run,
+                                // one record at a time; 2 = warp per run, 4 records batched; 0 = choose
+  int use_kernel = 3;           // ... the one chosen for the most recent epoch
+  int opt_ring = 1;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose:
+                                // 1 when the staleness budget limits the launch, else 2)
+  int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,
                                 // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t
+  int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)
   int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
-  int last_grid = 0, last_threads = 0;  // launch shape of the most recent epoch kernel
+  int last_grid = 0, last_threads = 0, last_ring = 0;  // launch shape of the most recent epoch kernel
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
   std::vector<Dataset> datasets;
@@ -125,7 +131,7 @@ struct LaunchShape {
   int grid, threads;
 };
 int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
-                       int inflight, float eta);
+                       double inflight, float eta);
 LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
                         double max_item_share, int64_t total_runs, int inflight = 6, float eta = 0.f);
 

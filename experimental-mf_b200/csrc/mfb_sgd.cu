@@ -400,10 +400,10 @@ int launch_sgd_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
     constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
     const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>
                                             : (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
-    if (LPR == 32 && VPL == 1 && c->opt_kernel == 2)  // b4 (below)
+    const bool b4 = LPR == 32 && VPL == 1 && c->use_kernel == 2;  // the batched kernel above
+    if (b4)
       k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel_b4<MFB_MODE_ATOMIC>
                                   : (const void*)sgd_epoch_kernel_b4<MFB_MODE_HOGWILD>;
-    const bool b4 = LPR == 32 && VPL == 1 && c->opt_kernel == 2;
     const LaunchShape ls = pick_launch(c, k, LPR, a.nruns - a.run_begin, d->max_item_share, d->nruns,
                                        b4 ? 8 : B, a.eta);
     void* args[] = {(void*)&a};
@@ -462,12 +462,35 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.ld_flavour = c->opt_memopt & 3;
   a.st_flavour = (c->opt_memopt >> 2) & 3;
   a.bias_flavour = (c->opt_memopt >> 4) & 3;
+  a.throttle = c->opt_throttle;
+  a.version = c->d_version;
+  a.probe_out = c->d_probe;
+  a.probe_item = c->probe_item;
   if (d->refresh_pending) {  // tiles are being re-sent from the host (mfb_dataset_refresh_from_host)
     MFB_CUDA(cudaStreamWaitEvent(c->stream, d->refreshed, 0));
     d->refresh_pending = false;
   }
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-  if (mode != MFB_MODE_ORDERED && c->opt_kernel == 3) {
+  // Which kernel.  The streaming sub-warp kernel needs the fewest instructions and L2 transactions
+  // per update and wins when the GPU can be filled.  When the bounds on concurrency (mfb_internal.h)
+  // leave only a few hundred user-runs in flight - a DSGD cell on one of many GPUs, the first
+  // epochs - throughput is (runs in flight) x (updates per second inside one run), and the
+  // warp-per-run kernel that advances four records of a run per step is faster per run
+  // (measured, Netflix shape: 3.3 vs 1.7 M updates/s per run at 840 runs; 0.87 vs 0.97 at 6720).
+  c->use_kernel = c->opt_kernel;
+  if (c->opt_kernel == 0) {
+    c->use_kernel = 3;
+    const int nvec = a.nvec;
+    if (mode != MFB_MODE_ORDERED && nvec > 16 && nvec <= 32) {
+      const int64_t runs = a.nruns - a.run_begin;
+      const int64_t cap = (int64_t)c->sm_count * 64;  // more than either kernel holds: bounds only
+      const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 0.6, eta), runs);
+      const double w_batch = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 8.0, eta), runs);
+      const double stream = std::min(w_stream * 1.2e6, 6.5e9), batch = std::min(w_batch * 3.0e6, 5.8e9);
+      if (batch > stream) c->use_kernel = 2;
+    }
+  }
+  if (mode != MFB_MODE_ORDERED && c->use_kernel == 3) {
     bool handled = false;
     const int rc = launch_sgd_stream(c, d, a, mode, &handled);
     if (rc != MFB_OK || handled) return rc;

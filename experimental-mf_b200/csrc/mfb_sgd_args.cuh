@@ -19,6 +19,13 @@ struct SgdArgs {
   int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
   float eta, lameta, lm1, gb;
   int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
+  int throttle;  // streaming kernel: wait for the previous record's bias atomic before the next reductions
+  // staleness probe (debug option "probe"): version[v] counts the updates of item v that the L2 has
+  // performed; probe_out[0..3] += {sum of (updates performed between my read and my update), updates,
+  // the same two restricted to item probe_item}
+  int* version;
+  unsigned long long* probe_out;
+  int probe_item;
 };
 
 struct Context;

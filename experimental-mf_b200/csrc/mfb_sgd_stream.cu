@@ -35,18 +35,21 @@ __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x,
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float4 cat4(const float2& a, const float2& b) { return make_float4(a.x, a.y, b.x, b.y); }
 
-// predicated (not branched) 128-bit fp32 reduction and bias reduction
-__device__ __forceinline__ void red_add4(float4* p, const float4& v, bool on) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
-      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)on)
-      : "memory");
-}
-__device__ __forceinline__ void red_add1(float* p, float v, bool on) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v),
-               "r"((int)on)
+__device__ __forceinline__ void red_add4(float4* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+__device__ __forceinline__ void red_add4p(float4* p, const float4& v, bool on) {
+  if (on) red_add4(p, v);
+}
+__device__ __forceinline__ void red_add1(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// the same with the old value returned: its arrival tells the issuer that the L2 has performed it
+__device__ __forceinline__ float atom_add1(float* p, float v) {
+  float old;
+  asm volatile("atom.global.add.f32 %0, [%1], %2;" : "=f"(old) : "l"(p), "f"(v) : "memory");
+  return old;
 }
 
 template <int LPR>
@@ -96,7 +99,8 @@ struct StreamSmem {
 
 }  // namespace
 
-template <int LPR, int VPL, int MODE, int R>
+// EXACT: the row is exactly LPR*VPL float4 (k = 32, 64, 128, 256, 512): no per-vector predicates.
+template <int LPR, int VPL, int MODE, int R, bool EXACT>
 __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const int nspans) {
   using SM = StreamSmem<LPR, VPL, R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
   float4* theta4 = reinterpret_cast<float4*>(a.theta);
   bool ok[VPL];  // this lane's vector i exists (rows whose length is not a multiple of LPR*4 floats)
 #pragma unroll
-  for (int i = 0; i < VPL; i++) ok[i] = gl + i * LPR < a.nvec;
+  for (int i = 0; i < VPL; i++) ok[i] = EXACT || gl + i * LPR < a.nvec;
   const float2 lameta2 = make_float2(a.lameta, a.lameta);
   const float2 lm12 = make_float2(a.lm1, a.lm1);
 
@@ -140,6 +144,13 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
   float bu = 0.f, pf_bu = 0.f;
   float fr[R];
   int fv[R];
+  int fver[R];                       // probe: version of the item when its row was gathered
+  unsigned long long pr_sum = 0, pr_n = 0, pr_hsum = 0, pr_hn = 0;
+#pragma unroll
+  for (int s = 0; s < R; s++) fver[s] = 0;
+  constexpr int U = R > 2 ? R : 2;   // steps per trip of the main loop; ring slot of step u is u % R
+  float ack[2] = {0.f, 0.f};         // values returned by the bias atomics of the last two updates
+  unsigned sink = 0;
 #pragma unroll
   for (int i = 0; i < VPL; i++) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -175,6 +186,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
         if (ok[i]) cp_async16(ring_me + (s * 32 * VPL + i * LPR) * 16, p + i * LPR);
       // the 16 aligned bytes around bv[v] (4-byte cp.async would go through L1, which is not coherent)
       if (gl == 0) cp_async16(bias_sub + s * SM::SUBS * 16, a.bv + (v & ~3));
+      if (a.version) fver[s] = __ldcg(a.version + v);
       jp++;
     }
   };
@@ -223,10 +235,11 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
     if (__all_sync(FULL, done)) break;
 
 #pragma unroll
-    for (int s = 0; s < R; s++) {
+    for (int u = 0; u < U; u++) {
+      const int s = u % R;
       cp_async_wait<R - 1>();  // the row gathered R steps ago (and everything older) has landed
       __syncwarp();            // ... for every lane: bias quads and record chunks are read across lanes
-      // ---- run switch (divergent, once per user-run) -----------------------------------------
+      // ---- run switch / span end (divergent, once per user-run) -------------------------------
       if (act && jc == cur_end) {
         if (ri >= 0) {  // retire the finished run
 #pragma unroll
@@ -234,44 +247,48 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
             if (ok[i]) __stcg(theta4 + (int64_t)uid * a.nvec + gl + i * LPR, t[i]);
           if (gl == 0) __stcg(a.bu + uid, bu);
         }
-        int nri = ri + 1;
-        int e = __shfl_sync(m, s_end, nri & (LPR - 1), LPR);
-        while (e == jc) {  // skip runs without records (jc < span_hi: a non-empty one follows)
-          nri++;
-          e = __shfl_sync(m, s_end, nri & (LPR - 1), LPR);
-        }
-        const bool reuse = (nri == pf_ri) && ri >= 0;
-        ri = nri;
-        cur_end = e;
-        const int nuid = __shfl_sync(m, s_uid, ri & (LPR - 1), LPR);
-        if (reuse && pf_same) {
-          // same user again: theta/bu continue in registers
-        } else if (reuse) {
-          if (step - pf_step < R) cp_async_wait<0>();  // prefetched less than R steps ago (short run)
-#pragma unroll
-          for (int i = 0; i < VPL; i++) t[i] = lds4(pft_me + i * LPR * 16);
-          bu = pf_bu;
+        if (jc == span_hi) {
+          act = false;  // a new span is claimed at the top of the outer loop
         } else {
+          int nri = ri + 1;
+          int e = __shfl_sync(m, s_end, nri & (LPR - 1), LPR);
+          while (e == jc) {  // skip runs without records (jc < span_hi: a non-empty one follows)
+            nri++;
+            e = __shfl_sync(m, s_end, nri & (LPR - 1), LPR);
+          }
+          const bool reuse = (nri == pf_ri) && ri >= 0;
+          ri = nri;
+          cur_end = e;
+          const int nuid = __shfl_sync(m, s_uid, ri & (LPR - 1), LPR);
+          if (reuse && pf_same) {
+            // same user again: theta/bu continue in registers
+          } else if (reuse) {
+            if (step - pf_step < R) cp_async_wait<0>();  // prefetched less than R steps ago (short run)
 #pragma unroll
-          for (int i = 0; i < VPL; i++)
-            t[i] = ok[i] ? __ldcg(theta4 + (int64_t)nuid * a.nvec + gl + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
-          bu = __ldcg(a.bu + nuid);
-        }
-        uid = nuid;
-        // fetch the next run's factor row now; it is needed one whole run from here
-        pf_ri = ri + 1;
-        if (pf_ri < span_n) {
-          const int puid = __shfl_sync(m, s_uid, pf_ri & (LPR - 1), LPR);
-          pf_same = (puid == uid);
-          if (!pf_same) {
+            for (int i = 0; i < VPL; i++) t[i] = lds4(pft_me + i * LPR * 16);
+            bu = pf_bu;
+          } else {
 #pragma unroll
             for (int i = 0; i < VPL; i++)
-              if (ok[i]) cp_async16(pft_me + i * LPR * 16, theta4 + (int64_t)puid * a.nvec + gl + i * LPR);
-            pf_bu = __ldcg(a.bu + puid);
-            pf_step = step;
+              t[i] = ok[i] ? __ldcg(theta4 + (int64_t)nuid * a.nvec + gl + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bu = __ldcg(a.bu + nuid);
           }
-        } else {
-          pf_ri = -1;
+          uid = nuid;
+          // fetch the next run's factor row now; it is needed one whole run from here
+          pf_ri = ri + 1;
+          if (pf_ri < span_n) {
+            const int puid = __shfl_sync(m, s_uid, pf_ri & (LPR - 1), LPR);
+            pf_same = (puid == uid);
+            if (!pf_same) {
+#pragma unroll
+              for (int i = 0; i < VPL; i++)
+                if (ok[i]) cp_async16(pft_me + i * LPR * 16, theta4 + (int64_t)puid * a.nvec + gl + i * LPR);
+              pf_bu = __ldcg(a.bu + puid);
+              pf_step = step;
+            }
+          } else {
+            pf_ri = -1;
+          }
         }
       }
 
@@ -292,61 +309,97 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
       const float e = a.eta * (fr[s] - d - bu - bvv - a.gb);
       const float2 e2 = make_float2(e, e);
       if (act) {
+        // Closed loop on the memory system: reductions are fire-and-forget, and when the L2 atomic
+        // units saturate they queue up - rows stay stale for longer than the ring accounts for
+        // (measured: divergence at a budget that is stable below saturation).  The bias update of a
+        // record is an atomic WITH return; waiting here for the one issued two steps ago keeps at
+        // most two records' reductions of this sub-warp queued behind the L2, and costs nothing
+        // while the L2 keeps up (the round trip overlaps a whole step).
+        if (a.throttle) sink ^= __float_as_uint(ack[u & 1]);
+        // the reductions come first: they end the window in which this row is stale elsewhere
         float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)fv[s] * a.nvec + gl;
+        const float2 keep = (MODE == MFB_MODE_ATOMIC) ? lm12 : lameta2;  // increment vs new value
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
-          const float2 tl = lo2(t[i]), th = hi2(t[i]), fl = lo2(f[i]), fh = hi2(f[i]);
-          float4 nf;
-          if (MODE == MFB_MODE_ATOMIC)  // increment of phi: (lameta-1)*phi + e*theta
-            nf = cat4(__ffma2_rn(e2, tl, __fmul2_rn(lm12, fl)), __ffma2_rn(e2, th, __fmul2_rn(lm12, fh)));
-          else
-            nf = cat4(__ffma2_rn(e2, tl, __fmul2_rn(lameta2, fl)), __ffma2_rn(e2, th, __fmul2_rn(lameta2, fh)));
-          t[i] = cat4(__ffma2_rn(e2, fl, __fmul2_rn(lameta2, tl)), __ffma2_rn(e2, fh, __fmul2_rn(lameta2, th)));
-          if (MODE == MFB_MODE_ATOMIC) red_add4(dst + i * LPR, nf, ok[i]);
-          else if (ok[i]) __stcg(dst + i * LPR, nf);
+          const float4 nf = cat4(__ffma2_rn(e2, lo2(t[i]), __fmul2_rn(keep, lo2(f[i]))),
+                                 __ffma2_rn(e2, hi2(t[i]), __fmul2_rn(keep, hi2(f[i]))));
+          if (MODE == MFB_MODE_ATOMIC) {
+            if (EXACT) red_add4(dst + i * LPR, nf);
+            else red_add4p(dst + i * LPR, nf, ok[i]);
+          } else if (ok[i]) {
+            __stcg(dst + i * LPR, nf);
+          }
         }
-        red_add1(a.bv + fv[s], fmaf(a.lm1, bvv, e), gl == 0);
+        if (gl == 0) ack[u & 1] = atom_add1(a.bv + fv[s], fmaf(a.lm1, bvv, e));
+        if (a.version && gl == 0) {
+          const int seen = atomicAdd(a.version + fv[s], 1) - fver[s];  // updates I did not see
+          pr_sum += (unsigned)seen;
+          pr_n++;
+          if (fv[s] == a.probe_item) {
+            pr_hsum += (unsigned)seen;
+            pr_hn++;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; i++)
+          t[i] = cat4(__ffma2_rn(e2, lo2(f[i]), __fmul2_rn(lameta2, lo2(t[i]))),
+                      __ffma2_rn(e2, hi2(f[i]), __fmul2_rn(lameta2, hi2(t[i]))));
         bu = fmaf(a.lameta, bu, e);
         jc++;
       }
       gather(s);  // refill the slot with record jc-1+R
       cp_async_commit();
       step++;
-      // ---- span end (divergent, once per LPR user-runs) ----------------------------------------
-      if (act && jc == span_hi) {
-#pragma unroll
-        for (int i = 0; i < VPL; i++)
-          if (ok[i]) __stcg(theta4 + (int64_t)uid * a.nvec + gl + i * LPR, t[i]);
-        if (gl == 0) __stcg(a.bu + uid, bu);
-        act = false;
-      }
     }
+  }
+  if (sink == 0x7fc0dead && a.nruns < 0) a.counter[1] = 1;  // never true: keeps the waits on `ack` alive
+  if (a.version && gl == 0) {
+    atomicAdd(a.probe_out + 0, pr_sum);
+    atomicAdd(a.probe_out + 1, pr_n);
+    atomicAdd(a.probe_out + 2, pr_hsum);
+    atomicAdd(a.probe_out + 3, pr_hn);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 namespace {
 
-// Launch shape.  `inflight` item rows are between gather and reduction at any instant:
-// sub-warps * R.  The hottest item (share p of the records) is therefore hit by inflight*p stale
-// updates at once, each applied with step eta: the product eta*inflight*p is what must stay bounded
+// Launch shape.  A sub-warp with a ring of R rows holds about R item rows between gather and
+// reduction (R = 1: the row is in flight for the L2 round trip plus the chain up to the reduction,
+// about 0.6 of a step).  The hottest item (share p of the records) is hit by inflight*p stale updates
+// at once, each applied with step eta: the product eta*inflight*p is what must stay bounded
 // (measured: divergence between 1.3 and 1.8 at eta = 0.02).  row_concurrency is that
 // bound expressed as a count at the reference's default eta = 0.02 (main.cc:97).
+template <int R>
+constexpr double ring_weight() { return R == 1 ? 0.6 : (double)R; }
+
+template <int LPR, int VPL, int R>
+int64_t stream_capacity(Context* c, const void* k) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * StreamSmem<LPR, VPL, R>::WARP_BYTES);
+  per_sm = std::max(per_sm, 1);
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  return (int64_t)c->sm_count * per_sm * 4 * (32 / LPR);  // sub-warps the hardware holds
+}
+
+template <int LPR, int VPL, int R>
+const void* stream_kernel(int mode, bool exact) {
+  return mode == MFB_MODE_ATOMIC
+             ? (exact ? (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_ATOMIC, R, true>
+                      : (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_ATOMIC, R, false>)
+             : (exact ? (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_HOGWILD, R, true>
+                      : (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_HOGWILD, R, false>);
+}
+
 template <int LPR, int VPL, int R>
 int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
-  const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_ATOMIC, R>
-                                          : (const void*)sgd_stream_kernel<LPR, VPL, MFB_MODE_HOGWILD, R>;
+  const void* k = stream_kernel<LPR, VPL, R>(mode, a.nvec == LPR * VPL);
   const int nruns = a.nruns - a.run_begin;
   const int nspans = (nruns + LPR - 1) / LPR;
   const int subs_per_warp = 32 / LPR;
   constexpr int WARP_BYTES = StreamSmem<LPR, VPL, R>::WARP_BYTES;
-  int per_sm = 0;
-  MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * WARP_BYTES));
-  per_sm = std::max(per_sm, 1);
-  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-  int64_t subs = (int64_t)c->sm_count * per_sm * 4 * subs_per_warp;  // what the hardware holds
-  subs = std::min<int64_t>(subs, std::max(nspans, 1));
-  subs = bounded_groups(c, subs, d->max_item_share, d->nruns, R, a.eta);
+  int64_t subs = std::min<int64_t>(stream_capacity<LPR, VPL, R>(c, k), std::max(nspans, 1));
+  subs = bounded_groups(c, subs, d->max_item_share, d->nruns, ring_weight<R>(), a.eta);
   // spread the warps over all SMs before stacking them: 1..4 warps per CTA
   const int64_t warps = (subs + subs_per_warp - 1) / subs_per_warp;
   int grid, threads;
@@ -361,6 +414,7 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   }
   c->last_grid = grid;
   c->last_threads = threads;
+  c->last_ring = R;
   void* args[] = {(void*)&a, (void*)&nspans};
   MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
   MFB_CUDA(cudaGetLastError());
@@ -370,11 +424,19 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
 
 template <int LPR, int VPL>
 int launch_stream_r(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
-  switch (c->opt_ring) {
+  int ring = c->opt_ring;
+  if (ring == 0) {
+    // R = 2 hides the L2 latency with half the warps; when the staleness budget (not the hardware)
+    // limits the launch, R = 1 gets more updates per second out of the same budget
+    const void* k2 = stream_kernel<LPR, VPL, 2>(mode, a.nvec == LPR * VPL);
+    const int64_t cap = std::min<int64_t>(stream_capacity<LPR, VPL, 2>(c, k2), std::max((a.nruns - a.run_begin + LPR - 1) / LPR, 1));
+    ring = bounded_groups(c, cap, d->max_item_share, d->nruns, 2.0, a.eta) < cap ? 1 : 2;
+  }
+  switch (ring) {
     case 1: return launch_stream_t<LPR, VPL, 1>(c, d, a, mode);
     case 2: return launch_stream_t<LPR, VPL, 2>(c, d, a, mode);
-    case 4: return launch_stream_t<LPR, VPL, 4>(c, d, a, mode);
-    default: return launch_stream_t<LPR, VPL, 3>(c, d, a, mode);
+    case 3: return launch_stream_t<LPR, VPL, 3>(c, d, a, mode);
+    default: return launch_stream_t<LPR, VPL, 4>(c, d, a, mode);
   }
 }
 

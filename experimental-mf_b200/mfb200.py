@@ -87,8 +87,11 @@ SIGNATURES = {
     "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
     "mfb_comm_allgather_items": (C.c_int, [C.c_void_p, i32p]),
     "mfb_comm_allreduce_sse": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "mfb_probe_arm": (C.c_int, [C.c_void_p, C.c_int]),
+    "mfb_probe_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "mfb_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "mfb_launch_count": (C.c_int64, [C.c_void_p]),
+    "mfb_last_launch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -447,8 +450,23 @@ class Context:
     def last_kernel_ms(self):
         return lib().mfb_last_kernel_ms(self.h)
 
+    def probe_arm(self, item):
+        _check(lib().mfb_probe_arm(self.h, int(item)))
+
+    def probe_read(self):
+        """(mean stale updates per update over all items, mean for the probed item, updates)"""
+        out = (C.c_uint64 * 4)()
+        _check(lib().mfb_probe_read(self.h, out))
+        s, n, hs, hn = [int(x) for x in out]
+        return s / max(n, 1), hs / max(hn, 1), n
+
     def launch_count(self):
         return lib().mfb_launch_count(self.h)
+
+    def last_launch(self):
+        out = (C.c_int * 4)()
+        _check(lib().mfb_last_launch(self.h, out))
+        return {"kernel": out[0], "grid": out[1], "threads": out[2], "ring": out[3]}
 
 
 def comm_unique_id():

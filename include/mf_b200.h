@@ -69,8 +69,12 @@ void mfb_destroy(mfb_ctx* ctx);
 /* run all work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int mfb_set_stream(mfb_ctx* ctx, void* cuda_stream);
 int mfb_sync(mfb_ctx* ctx);
-/* tuning knobs (DESIGN.md "concurrency bound"): "row_concurrency" (default 8), "run_fraction_ppm"
- * (default 3500), "max_groups", "ctas_per_sm", "threads", "memopt" */
+/* tuning knobs (DESIGN.md "concurrency bounds"): "row_concurrency" (default 32: bound on the stale
+ * updates of the hottest item row in flight at once, at eta = 0.02), "eta_scaling" (1: that bound
+ * widens with 0.02/eta; 2: the run bound too; 0: off), "run_fraction_ppm" (default 3500: user-runs in
+ * flight / user-runs of the file), "max_groups" (explicit number of runs in flight), "kernel" (0 =
+ * choose, 1/2 = warp per run, 3 = sub-warp stream), "ring" (1..4), "throttle", "ctas_per_sm",
+ * "threads", "memopt" */
 int mfb_set_option(mfb_ctx* ctx, const char* name, int value);
 /* allocate the optional array groups: 1 = admf shadows (*_OLD), 2 = dpmf (UR, VR, LAMBDA_*) */
 int mfb_enable(mfb_ctx* ctx, int group);
@@ -236,10 +240,20 @@ int mfb_comm_allgather_items(mfb_ctx* ctx, const int32_t* item_bounds);
 /* sum (sse, n) over the ranks */
 int mfb_comm_allreduce_sse(mfb_ctx* ctx, double* sse, int64_t* n);
 
+/* Staleness probe of the parallel SGD schedule (diagnostic): with the probe armed (item >= 0; item < 0
+ * disarms) every update also counts, per item, the updates the L2 has performed, and records how
+ * many updates of the same item happened between the read of its row and the update.
+ * mfb_probe_read: out = {stale updates summed over all updates, number of updates, the same two
+ * for the probed item}; the counters restart. */
+int mfb_probe_arm(mfb_ctx* ctx, int item);
+int mfb_probe_read(mfb_ctx* ctx, uint64_t out[4]);
+
 /* device time in ms of the most recent epoch / sse call's kernels (CUDA events on the
  * context's stream; valid after mfb_sync) and the number of kernel launches since create */
 float mfb_last_kernel_ms(mfb_ctx* ctx);
 int64_t mfb_launch_count(mfb_ctx* ctx);
+/* shape of the most recent SGD epoch launch: out = {kernel variant, grid, threads per CTA, ring depth} */
+int mfb_last_launch(mfb_ctx* ctx, int out[4]);
 
 #ifdef __cplusplus
 }

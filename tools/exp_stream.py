@@ -16,18 +16,19 @@ def timing(full=True):
     tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz))
     c = mb.Context(nu, nv, k)
     dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
-    cfgs = [(2, 0, 48, 1)]
-    for ring in (2, 3, 4):
+    cfgs = []
+    for thr in (0, 1):
         for rc in (24, 48, 96):
-            cfgs.append((3, ring, rc, 1))
-    cfgs += [(3, 3, 48, 0), (3, 3, 0, 0)]
-    for kern, ring, rc, esc in cfgs:
-        c.set_option("kernel", kern); c.set_option("row_concurrency", rc); c.set_option("eta_scaling", esc)
-        if ring: c.set_option("ring", ring)
+            for ring in (1, 2):
+                cfgs.append((3, ring, rc, 1, thr))
+    cfgs += [(3, 1, 6, 1, 1), (3, 1, 12, 1, 1)]
+    for kern, ring, rc, esc, thr in cfgs:
+        c.set_option("kernel", kern); c.set_option("row_concurrency", rc); c.set_option("eta_scaling", esc); c.set_option("throttle", thr)
+        c.set_option("ring", ring)
         c.init_normal(1, 1e-2)
         ms, rmse = run(c, dtr, dte, tr.nratings)
-        print("full kernel %d ring %d rc %3d eta_scaling %d: ms %s  best %.2f Gupd/s  rmse(4 ep) %.4f" % (
-            kern, ring, rc, esc, " ".join("%.2f" % x for x in ms), tr.nratings / min(ms) / 1e6, rmse), flush=True)
+        print("full kernel %d ring %d rc %3d eta_scaling %d throttle %d: ms %s  best %.2f Gupd/s  rmse(4 ep) %.4f" % (
+            kern, ring, rc, esc, thr, " ".join("%.2f" % x for x in ms), tr.nratings / min(ms) / 1e6, rmse), flush=True)
     c.close()
 def accuracy():
     nu, nv, nnz, k, EPOCHS = 120000, 17770, 25_000_000, 128, 8
@@ -36,11 +37,12 @@ def accuracy():
     test = ol.Dataset(te.block_off, te.run_uid, te.run_off, te.vid, te.rating)
     m = ol.Model(nu, nv, k, seed=11); th, ph = m.dense()
     res = {}
-    for kern, ring, rc, esc in [(3, 3, 24, 1), (3, 3, 48, 1), (3, 3, 64, 1), (3, 3, 96, 1), (3, 2, 48, 1), (3, 4, 48, 1), (3, 3, 48, 0)]:
+    for kern, ring, rc, esc in [(3, 1, 32, 1), (3, 1, 32, 2), (3, 1, 64, 2), (3, 2, 32, 2)]:
         c = mb.Context(nu, nv, k); c.set_factors(th, ph, m.bu, m.bv)
         c.set_option("kernel", kern); c.set_option("row_concurrency", rc); c.set_option("ring", ring); c.set_option("eta_scaling", esc)
         dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
         traj, ms = [], []
+        if len(sys.argv) > 2: c.set_option("run_fraction_ppm", int(sys.argv[2]))
         for ep in range(1, EPOCHS + 1):
             c.sgd_epoch(dtr, mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ATOMIC); ms.append(c.last_kernel_ms()); traj.append(c.rmse(dte, GB))
         res[(kern, ring, rc, esc)] = traj

@@ -1,0 +1,44 @@
+"""CPU study (oracle only): is the test-RMSE gap of the parallel schedule an ORDER effect?
+The serial oracle is run on the medium shape (120k x 17,770, 25M ratings, k=128) in file order and
+on the same records re-ordered as W user-runs interleaved record by record (every update
+immediately visible: no staleness at all, only a different sequential order)."""
+import ctypes as C, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "experimental-mf_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mfb200 as mb, oraclelib as ol
+GB = 2.76
+nu, nv, nnz, k, EPOCHS = 120000, 17770, 25_000_000, 128, int(os.environ.get("EPOCHS", "8"))
+tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz))
+test = ol.Dataset(te.block_off, te.run_uid, te.run_off, te.vid, te.rating)
+run_off = np.asarray(tr.run_off, np.int64); run_uid = np.asarray(tr.run_uid); vid = np.asarray(tr.vid); rating = np.asarray(tr.rating)
+nruns = len(run_uid); n = len(vid)
+rec_run = np.repeat(np.arange(nruns, dtype=np.int64), np.diff(run_off))
+rec_pos = np.arange(n, dtype=np.int64) - run_off[rec_run]
+def interleaved(W):
+    """W slots, each advancing one record per round; a slot that finishes its run takes the next
+    run of the file (what the device-side queue does)."""
+    if W <= 1:
+        return ol.Dataset(tr.block_off, run_uid, run_off, vid, rating)
+    import heapq
+    lens = np.diff(run_off)
+    heap = [(0, s) for s in range(W)]
+    start = np.zeros(nruns, np.int64); slot = np.zeros(nruns, np.int64)
+    for r in range(nruns):
+        t, sl = heapq.heappop(heap)
+        start[r], slot[r] = t, sl
+        heapq.heappush(heap, (t + int(lens[r]), sl))
+    key = (start[rec_run] + rec_pos) * (1 << 20) + slot[rec_run]
+    order = np.argsort(key, kind="stable")
+    return ol.Dataset(np.array([0, n], np.int64), run_uid[rec_run[order]].astype(np.int32), np.arange(n + 1, dtype=np.int64),
+                      vid[order], rating[order])
+for W in [int(x) for x in (sys.argv[1:] or ["1", "1680", "6720"])]:
+    ds = interleaved(W)
+    m = ol.Model(nu, nv, k, seed=11)
+    mm, dd, tt = m.as_mfo(), ds.as_mfo(), test.as_mfo()
+    traj = []
+    t0 = time.time()
+    for ep in range(1, EPOCHS + 1):
+        ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
+        cnt = C.c_int64(); s = ol.oracle().mfo_sse(C.byref(mm), C.byref(tt), GB, C.byref(cnt)); traj.append(float(np.sqrt(s / cnt.value)))
+    print("W %5d: rmse %s  (%.0f s)" % (W, " ".join("%.4f" % x for x in traj), time.time() - t0), flush=True)
