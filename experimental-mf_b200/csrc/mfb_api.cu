@@ -266,8 +266,11 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
   } else if (!strcmp(name, "kernel")) {
-    MFB_REQUIRE(value >= 0 && value <= 3, "kernel must be 0 (choose), 1, 2 or 3");
+    MFB_REQUIRE(value >= 0 && value <= 4, "kernel must be 0 (choose), 1, 2, 3 or 4");
     c->opt_kernel = value;
+  } else if (!strcmp(name, "batch")) {
+    MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
+    c->opt_batch = value;
   } else if (!strcmp(name, "ring")) {
     MFB_REQUIRE(value >= 0 && value <= 4, "ring must be 0..4");
     c->opt_ring = value;

@@ -98,8 +98,10 @@ struct Context {
   // options
   int opt_ctas_per_sm = 0, opt_threads = 256, opt_batch = 4, opt_memopt = 0;
   int opt_kernel = 0;           // SGD kernel: 3 = sub-warp streaming (mfb_sgd_stream.cu); 1 = warp per run,
-                                // one record at a time; 2 = warp per run, 4 records batched; 0 = choose
+                                // one record at a time; 2 = warp per run, 4 records batched; 4 = burst
+                                // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
+  double rate_stream = 1.2e6, rate_burst = 3.5e6;  // updates/s per run in flight (measured; for the choice)
   int opt_ring = 1;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose:
                                 // 1 when the staleness budget limits the launch, else 2)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,

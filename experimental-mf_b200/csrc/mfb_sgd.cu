@@ -475,8 +475,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   // per update and wins when the GPU can be filled.  When the bounds on concurrency (mfb_internal.h)
   // leave only a few hundred user-runs in flight - a DSGD cell on one of many GPUs, the first
   // epochs - throughput is (runs in flight) x (updates per second inside one run), and the
-  // warp-per-run kernel that advances four records of a run per step is faster per run
-  // (measured, Netflix shape: 3.3 vs 1.7 M updates/s per run at 840 runs; 0.87 vs 0.97 at 6720).
+  // warp-per-run burst kernel (mfb_sgd_burst.cu) is several times faster per run.
   c->use_kernel = c->opt_kernel;
   if (c->opt_kernel == 0) {
     c->use_kernel = 3;
@@ -485,10 +484,16 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
       const int64_t runs = a.nruns - a.run_begin;
       const int64_t cap = (int64_t)c->sm_count * 64;  // more than either kernel holds: bounds only
       const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 0.6, eta), runs);
-      const double w_batch = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 8.0, eta), runs);
-      const double stream = std::min(w_stream * 1.2e6, 6.5e9), batch = std::min(w_batch * 3.0e6, 5.8e9);
-      if (batch > stream) c->use_kernel = 2;
+      const double w_burst = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 8.0, eta), (runs + 31) / 32);
+      const double stream = std::min(w_stream * c->rate_stream, 6.5e9), burst = std::min(w_burst * c->rate_burst, 5.8e9);
+      if (burst > stream) c->use_kernel = 4;
     }
+  }
+  if (mode != MFB_MODE_ORDERED && c->use_kernel == 4) {
+    bool handled = false;
+    const int rc = launch_sgd_burst(c, d, a, mode, &handled);
+    if (rc != MFB_OK || handled) return rc;
+    c->use_kernel = 3;
   }
   if (mode != MFB_MODE_ORDERED && c->use_kernel == 3) {
     bool handled = false;

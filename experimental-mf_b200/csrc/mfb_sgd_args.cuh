@@ -33,6 +33,9 @@ struct Dataset;
 // mfb_sgd_stream.cu: the sub-warp streaming kernel (production schedule); returns MFB_OK or an
 // error; `handled` is false when the row shape has no streaming instantiation
 int launch_sgd_stream(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled);
+// mfb_sgd_burst.cu: warp per run, B records per step, everything requested one batch ahead (the
+// kernel for launches that the concurrency bounds keep narrow)
+int launch_sgd_burst(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled);
 
 }  // namespace mfb
 #endif

@@ -1,0 +1,347 @@
+// sgd_burst_kernel - plain-SGD epoch (SgdFilter::operator(), mf.h:76-132) for the regime in which
+// only a few hundred user-runs may be in flight per GPU (a DSGD cell on one of many GPUs, the first
+// epochs of a file with hot items; bounds: mfb_internal.h).  Throughput is then
+//     (runs in flight) x (updates per second inside ONE run),
+// and a run is a sequential chain through theta_u.  This kernel shortens that chain:
+//
+//  * one warp per run, one float4 of the row per lane (k <= 128);
+//  * B consecutive records of the run are advanced together, with the result of updating them one
+//    after the other in exact arithmetic:
+//        theta^b = lameta*theta^(b-1) + e_b*phi_b  =>
+//        <theta^(b-1), phi_b> = lameta^b <theta^0, phi_b> + sum_{a<b} lameta^(b-1-a) e_a <phi_a, phi_b>
+//    so the B + B(B-1)/2 inner products <theta^0,phi_b>, <phi_a,phi_b> are reduced TOGETHER (5 shuffle
+//    rounds for all of them), e_1..e_B follow from a scalar recurrence (4 dependent operations per
+//    record), and the row updates are straight vector FMAs + reductions.  (Records of one run are
+//    distinct items - getdata.cc groups a user's ratings - so no phi row appears twice in a batch.)
+//  * everything the next batch needs is requested one batch ahead - its item rows and biases, across
+//    run boundaries; the factor row of the next user one run ahead; the record ids/ratings 32 records
+//    ahead - by cp.async (LDGSTS) into shared memory, retired in order by cp.async.wait_group.  With
+//    plain loads into registers nothing overlaps: ptxas tracks every LDG (and the shuffles) of the
+//    loop on one scoreboard slot, so the first use of the CURRENT batch waits for the requests of
+//    the NEXT one (measured: 2k cycles per batch of four).
+//  * a warp walks a span of 32 consecutive runs: lane l keeps the user id and end of run l.
+#include <algorithm>
+
+#include "mfb_internal.h"
+#include "mfb_sgd_args.cuh"
+
+namespace mfb {
+
+namespace {
+
+__device__ __forceinline__ float dot4(const float4& x, const float4& y) {
+  const float2 p = __ffma2_rn(make_float2(x.x, x.y), make_float2(y.x, y.y),
+                              __fmul2_rn(make_float2(x.z, x.w), make_float2(y.z, y.w)));
+  return p.x + p.y;
+}
+// a*x + b*y on four lanes
+__device__ __forceinline__ float4 axpby4(float a, const float4& x, float b, const float4& y) {
+  const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+  const float2 lo = __ffma2_rn(a2, make_float2(x.x, x.y), __fmul2_rn(b2, make_float2(y.x, y.y)));
+  const float2 hi = __ffma2_rn(a2, make_float2(x.z, x.w), __fmul2_rn(b2, make_float2(y.z, y.w)));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {  // L2 only (.cg)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {  // immutable data (.ca)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds1i(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void burst_red4(float4* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void burst_red1(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+}  // namespace
+
+// shared memory of one warp: two slots of (B item rows + B bias quads), two chunks of 32 record
+// ids/ratings, the prefetched factor row and bias quad of the next user
+template <int B>
+struct BurstSmem {
+  static constexpr int ROWS = 2 * B * 512;   // [slot][b][lane] float4
+  static constexpr int BIAS = 2 * B * 16;    // [slot][b] the 16 aligned bytes around bv[v]
+  static constexpr int CHUNK = 2 * 256;      // [buf][vid 32 x int | rating 32 x float]
+  static constexpr int PFT = 512 + 16;       // next user's row + the 16 aligned bytes around bu[u]
+  static constexpr int WARP_BYTES = ROWS + BIAS + CHUNK + PFT;
+};
+
+template <int B, int MODE>
+__global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const int nspans) {
+  using SM = BurstSmem<B>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool lane_ok = lane < a.nvec;
+  const float4* __restrict__ phi4 = reinterpret_cast<const float4*>(a.phi);
+  float4* theta4 = reinterpret_cast<float4*>(a.theta);
+  const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + (threadIdx.x >> 5) * SM::WARP_BYTES;
+  const uint32_t rows_me = wbase + lane * 16;           // + (slot*B + b)*512
+  const uint32_t bias0 = wbase + SM::ROWS;              // + (slot*B + b)*16
+  const uint32_t chunk0 = bias0 + SM::BIAS;             // + buf*256 (+128: ratings)
+  const uint32_t pft_me = chunk0 + SM::CHUNK + lane * 16;
+  const uint32_t pfb = chunk0 + SM::CHUNK + 512;
+  {  // lanes beyond the row length never copy: their vectors must read as zeros
+    float4* w = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * SM::WARP_BYTES);
+    for (int q = lane; q < SM::WARP_BYTES / 16; q += 32) w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  }
+  int iter = 0;  // iterations of the batch loop = cp.async groups committed there
+
+  for (;;) {
+    // ---- claim a span of 32 consecutive user-runs ---------------------------------------------
+    int sp = 0;
+    if (lane == 0) sp = atomicAdd(a.counter, 1);
+    sp = __shfl_sync(FULL, sp, 0);
+    if (sp >= nspans) break;
+    const int run0 = a.run_begin + sp * 32;
+    const int span_n = min(32, a.nruns - run0);
+    int s_uid = 0, s_end = 0;
+    if (lane < span_n) {
+      s_uid = __ldg(a.run_uid + run0 + lane);
+      s_end = __ldg(a.run_off + run0 + lane + 1);
+    }
+    const int span_lo = __ldg(a.run_off + run0);
+    const int span_hi = __shfl_sync(FULL, s_end, span_n - 1);
+    if (span_lo >= span_hi) continue;
+
+    // records [cbase, cbase+32) are in chunk buffer cbuf, the next 32 in the other one
+    int cbase = span_lo, cbuf = 0;
+    auto chunk_fetch = [&](int buf, int q0) {
+      const int q = q0 + lane;
+      if (q < span_hi) {
+        cp_async4(chunk0 + buf * 256 + lane * 4, a.vid + q);
+        cp_async4(chunk0 + buf * 256 + 128 + lane * 4, a.rating + q);
+      }
+    };
+    chunk_fetch(0, span_lo);
+    chunk_fetch(1, span_lo + 32);
+    // first non-empty run: its factor row comes through the same path as the prefetched ones
+    int ri = -1, cur_end = span_lo, uid = -1;
+    int nri = 0, n_end = 0, n_uid = -1, pf_iter = 0;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bu = 0.f;
+    // find the next non-empty run after ri (runs without records share their predecessor's end)
+    // and request its factor row and bias
+    auto prefetch_next_run = [&]() {
+      n_end = nri < span_n ? __shfl_sync(FULL, s_end, nri & 31) : 0;
+      while (nri < span_n && n_end == cur_end) {
+        nri++;
+        n_end = nri < span_n ? __shfl_sync(FULL, s_end, nri & 31) : 0;
+      }
+      if (nri < span_n) {
+        n_uid = __shfl_sync(FULL, s_uid, nri);
+        if (n_uid != uid) {  // (the same user again continues in registers)
+          if (lane_ok) cp_async16(pft_me, theta4 + (int64_t)n_uid * a.nvec + lane);
+          if (lane == 0) cp_async16(pfb, a.bu + (n_uid & ~3));
+          pf_iter = iter;
+        }
+      }
+    };
+    prefetch_next_run();
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // request the rows and bias quads of the batch [j0, j0+n) into slot p; ids/ratings -> registers
+    auto request = [&](int p, int j0, int n, int (&vv)[B], float (&rr)[B]) {
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        const int idx = (j0 - cbase + b) & 31;
+        vv[b] = lds1i(chunk0 + cbuf * 256 + idx * 4);
+        rr[b] = lds1(chunk0 + cbuf * 256 + 128 + idx * 4);
+        if (b < n) {
+          if (lane_ok) cp_async16(rows_me + (p * B + b) * 512, phi4 + (int64_t)vv[b] * a.nvec + lane);
+          if (lane == 0) cp_async16(bias0 + (p * B + b) * 16, a.bv + (vv[b] & ~3));
+        }
+      }
+    };
+
+    int j = span_lo, p = 0;
+    bool cur_new_run = true;  // the current batch opens run nri
+    int nb = min(B, min(n_end, cbase + 32) - j);
+    int v[B];
+    float r[B];
+    request(0, j, nb, v, r);
+    cp_async_commit();
+
+    for (;;) {
+      // ---- run switch: the batch about to be computed opens run nri ----------------------------------
+      if (cur_new_run) {
+        if (ri >= 0) {
+          if (lane_ok) __stcg(theta4 + (int64_t)uid * a.nvec + lane, t);
+          if (lane == 0) __stcg(a.bu + uid, bu);
+        }
+        if (n_uid != uid) {
+          if (iter - pf_iter < 2) {  // requested less than two batches ago (a run of one batch)
+            cp_async_wait<0>();
+            __syncwarp();
+          }
+          t = lds4(pft_me);
+          bu = lds1(pfb + (n_uid & 3) * 4);
+        }
+        uid = n_uid;
+        ri = nri;
+        cur_end = n_end;
+        nri = ri + 1;
+        prefetch_next_run();
+      }
+      // ---- request the next batch [j1, j1+nb1) while this one is computed -------------------------
+      const int j1 = j + nb;
+      const bool more = j1 < span_hi;
+      const bool next_new_run = more && j1 == cur_end;
+      int nb1 = 0;
+      int vn[B];
+      float rn[B];
+      if (more) {
+        if (j1 == cbase + 32) {  // the other buffer holds the next 32 records; refill this one
+          chunk_fetch(cbuf, cbase + 64);
+          cbuf ^= 1;
+          cbase += 32;
+        }
+        nb1 = min(B, min(next_new_run ? n_end : cur_end, cbase + 32) - j1);
+        request(p ^ 1, j1, nb1, vn, rn);
+      }
+      cp_async_commit();
+      iter++;
+      cp_async_wait<1>();  // everything but the requests just made has landed
+      __syncwarp();
+
+      // ---- this batch: all inner products at once ---------------------------------------------------
+      float4 f[B];
+      float bvv[B];
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        f[b] = lds4(rows_me + (p * B + b) * 512);
+        bvv[b] = lds1(bias0 + (p * B + b) * 16 + (v[b] & 3) * 4);
+      }
+      float D[B], G[B][B];
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        D[b] = dot4(t, f[b]);
+#pragma unroll
+        for (int c = b + 1; c < B; c++) G[b][c] = dot4(f[b], f[c]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+          D[b] += __shfl_xor_sync(FULL, D[b], o);
+#pragma unroll
+          for (int c = b + 1; c < B; c++) G[b][c] += __shfl_xor_sync(FULL, G[b][c], o);
+        }
+      }
+      // ---- residuals by recurrence, row updates ------------------------------------------------------
+      float coef[B];
+      float tpow = 1.0f;
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        if (b < nb) {
+          float d = tpow * D[b];
+#pragma unroll
+          for (int c = 0; c < b; c++) d = fmaf(coef[c], G[c][b], d);
+          const float e = a.eta * (((r[b] - bvv[b] - a.gb) - d) - bu);
+          float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)v[b] * a.nvec + lane;
+          if (MODE == MFB_MODE_ATOMIC) {  // increment of phi_b, from theta BEFORE this record
+            const float4 nf = axpby4(e, t, a.lm1, f[b]);
+            if (lane_ok) burst_red4(dst, nf);
+          } else {
+            const float4 nf = axpby4(e, t, a.lameta, f[b]);
+            if (lane_ok) __stcg(dst, nf);
+          }
+          if (lane == 0) burst_red1(a.bv + v[b], fmaf(a.lm1, bvv[b], e));
+          t = axpby4(e, f[b], a.lameta, t);
+          bu = fmaf(a.lameta, bu, e);
+#pragma unroll
+          for (int c = 0; c < b; c++) coef[c] *= a.lameta;
+          coef[b] = e;
+          tpow *= a.lameta;
+        }
+      }
+
+      if (!more) break;
+      j = j1;
+      nb = nb1;
+      p ^= 1;
+      cur_new_run = next_new_run;
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        r[b] = rn[b];
+        v[b] = vn[b];
+      }
+    }
+    // last run of the span
+    if (lane_ok) __stcg(theta4 + (int64_t)uid * a.nvec + lane, t);
+    if (lane == 0) __stcg(a.bu + uid, bu);
+    cp_async_wait<0>();  // nothing of this span may land in the buffers of the next one
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+
+template <int B>
+int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
+  const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC>
+                                          : (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD>;
+  const int nruns = a.nruns - a.run_begin;
+  const int nspans = (nruns + 31) / 32;
+  int per_sm = 0;
+  constexpr int WARP_BYTES = BurstSmem<B>::WARP_BYTES;
+  MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * WARP_BYTES));
+  per_sm = std::max(per_sm, 1);
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max(nspans, 1));
+  // a run holds the current batch and the requested one: 2B item rows between gather and reduction
+  warps = bounded_groups(c, warps, d->max_item_share, d->nruns, 2.0 * B, a.eta);
+  int grid, threads;
+  if (warps <= c->sm_count) {
+    grid = (int)warps;
+    threads = 32;
+  } else {
+    const int64_t per = (warps + c->sm_count - 1) / c->sm_count;
+    const int ctas = (int)((per + 3) / 4);
+    threads = 32 * (int)((per + ctas - 1) / ctas);
+    grid = c->sm_count * ctas;
+  }
+  c->last_grid = grid;
+  c->last_threads = threads;
+  c->last_ring = B;
+  void* args[] = {(void*)&a, (void*)&nspans};
+  MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
+  MFB_CUDA(cudaGetLastError());
+  c->launches++;
+  return MFB_OK;
+}
+
+}  // namespace
+
+int launch_sgd_burst(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled) {
+  *handled = a.nvec > 16 && a.nvec <= 32;  // rows of 68..128 floats: one float4 per lane
+  if (!*handled) return MFB_OK;
+  if (c->opt_batch == 8) return launch_burst_t<8>(c, d, a, mode);
+  return launch_burst_t<4>(c, d, a, mode);
+}
+
+}  // namespace mfb

@@ -61,9 +61,21 @@ def test_ordered_sgd_matches_oracle_all_row_shapes(dim):
     c.close()
 
 
+KERNELS = [(3, 1), (3, 2), (3, 4), (4, 4), (4, 8), (2, 0)]  # (kernel, ring depth / batch size)
+
+
+def pick_kernel(c, kernel, depth):
+    c.set_option("kernel", kernel)
+    if kernel == 3:
+        c.set_option("ring", depth)
+    if kernel == 4:
+        c.set_option("batch", depth)
+
+
+@pytest.mark.parametrize("kernel,depth", KERNELS)
 @pytest.mark.parametrize("mode", [mb.MODE_HOGWILD, mb.MODE_ATOMIC])
-@pytest.mark.parametrize("dim", [16, 32, 64, 128, 256])
-def test_parallel_modes_exact_on_conflict_free_data(mode, dim):
+@pytest.mark.parametrize("dim", [16, 32, 64, 100, 128, 256])
+def test_parallel_modes_exact_on_conflict_free_data(mode, dim, kernel, depth):
     """Size-independent property: when no two ratings share a user or an item the update order
     cannot matter, so the parallel schedules must agree with the serial oracle (up to the
     fused-multiply-add / butterfly-sum rounding of the fast path)."""
@@ -75,6 +87,7 @@ def test_parallel_modes_exact_on_conflict_free_data(mode, dim):
     c = ctx_from_model(m)
     c.set_option("row_concurrency", 0)  # full machine width
     c.set_option("run_fraction_ppm", 0)
+    pick_kernel(c, kernel, depth)
     d = upload_ds(c, ds)
     c.sgd_epoch(d, 0.05, 0.02, GB, mode)
     oracle_sgd(m, ds, 0.05, 0.02, GB)
@@ -82,14 +95,17 @@ def test_parallel_modes_exact_on_conflict_free_data(mode, dim):
     c.close()
 
 
+@pytest.mark.parametrize("kernel,depth", KERNELS)
 @pytest.mark.parametrize("mode", [mb.MODE_HOGWILD, mb.MODE_ATOMIC])
-@pytest.mark.parametrize("dim", [16, 32, 64, 128])
-def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim):
-    """Ragged user-runs (1..70 records, so sub-warps of one warp diverge) over items that each occur
-    once: phi updates cannot conflict, theta is sequential inside its run => must equal the oracle."""
+@pytest.mark.parametrize("dim", [16, 32, 64, 100, 128])
+def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim, kernel, depth):
+    """Ragged user-runs (0..70 records, so sub-warps of one warp diverge, batches are partial and some
+    runs are empty) over items that each occur once: phi updates cannot conflict, theta is sequential
+    inside its run => must equal the oracle (the batched kernels up to the rounding of the Gram
+    recurrence)."""
     rng = np.random.default_rng(dim + mode)
     nu = 3000
-    lens = rng.integers(1, 71, nu)
+    lens = rng.integers(0, 71, nu)
     n = int(lens.sum())
     run_off = np.r_[0, np.cumsum(lens)]
     ds = ol.Dataset(np.r_[np.arange(0, nu, 100), nu], rng.permutation(nu), run_off, rng.permutation(n),
@@ -98,6 +114,7 @@ def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim):
     c = ctx_from_model(m)
     c.set_option("row_concurrency", 0)  # full machine width
     c.set_option("run_fraction_ppm", 0)
+    pick_kernel(c, kernel, depth)
     d = upload_ds(c, ds)
     c.sgd_epoch(d, 0.05, 0.02, GB, mode)
     oracle_sgd(m, ds, 0.05, 0.02, GB)

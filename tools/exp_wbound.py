@@ -10,10 +10,11 @@ nu, nv, nnz, k = 480189, 17770, 100_000_000, 128
 tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz))
 c = mb.Context(nu, nv, k)
 dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
-for W in (840, 1680, 3360, 6720):
-    for kern, ring in ((1, 0), (2, 0), (3, 1), (3, 2), (3, 4)):
+for W in (210, 420, 840, 1680, 3360):
+    for kern, ring in ((2, 0), (3, 2), (4, 4), (4, 8)):
         c.set_option("kernel", kern); c.set_option("max_groups", W)
-        if ring: c.set_option("ring", ring)
+        if kern == 3: c.set_option("ring", ring)
+        if kern == 4: c.set_option("batch", ring)
         c.init_normal(1, 1e-2)
         ms = []
         for ep in (1, 2):

@@ -13,6 +13,17 @@ tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz))
 test = ol.Dataset(te.block_off, te.run_uid, te.run_off, te.vid, te.rating)
 run_off = np.asarray(tr.run_off, np.int64); run_uid = np.asarray(tr.run_uid); vid = np.asarray(tr.vid); rating = np.asarray(tr.rating)
 nruns = len(run_uid); n = len(vid)
+if os.environ.get("MERGE"):  # one run per user: its runs concatenated, users in order of first appearance
+    rec_run0 = np.repeat(np.arange(nruns, dtype=np.int64), np.diff(run_off))
+    first = np.full(nu, nruns, np.int64); np.minimum.at(first, run_uid, np.arange(nruns))
+    rank = np.empty(nu, np.int64); rank[np.argsort(first, kind="stable")] = np.arange(nu)
+    order0 = np.argsort(rank[run_uid[rec_run0]], kind="stable")
+    vid, rating = vid[order0], rating[order0]
+    u_sorted = run_uid[rec_run0][order0]
+    starts = np.r_[0, np.flatnonzero(np.diff(u_sorted)) + 1]
+    run_uid = u_sorted[starts].astype(np.int32); run_off = np.r_[starts, n].astype(np.int64); nruns = len(run_uid)
+    tr = ol.Dataset(np.array([0, nruns], np.int64), run_uid, run_off, vid, rating)
+    print("merged: %d runs" % nruns, flush=True)
 rec_run = np.repeat(np.arange(nruns, dtype=np.int64), np.diff(run_off))
 rec_pos = np.arange(n, dtype=np.int64) - run_off[rec_run]
 def interleaved(W):
