@@ -44,10 +44,14 @@ def bytes_per_update(k):
     return 12 + 16 * k  # rating record + two factor rows read and written
 
 
+KERNEL_NAMES = {1: "sgd_epoch_kernel (warp per run)", 2: "sgd_epoch_kernel_b4 (warp per run, 4 records per step)",
+                3: "sgd_stream_kernel (sub-warp per run, cp.async ring)", 4: "sgd_burst_kernel (warp per run, Gram-batched)"}
+
+
 def profiled_traffic(schedule):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the update kernel, from the
     committed ncu --set full capture of this same command (profiles/, made by tools/ncu_summary.py)."""
-    p = os.path.join(ROOT, "profiles", "r1_sgd_%s.json" % schedule)
+    p = os.path.join(ROOT, "profiles", "r1_sgd_stream.json" if schedule == "atomic" else "r1_sgd_%s.json" % schedule)
     try:
         return float(json.load(open(p))["launches"][0]["dram_traffic_bytes"]), os.path.relpath(p, ROOT)
     except (OSError, KeyError, IndexError, ValueError):
@@ -197,6 +201,8 @@ def workload_config(wl, n_gpus):
     return {"workload": "%s-shaped synthetic (%d users x %d items, %d ratings) SGD MF k=%d fp32" % (wl, nu, nv, nnz, k),
             "nu": nu, "nv": nv, "ratings": nnz, "k": k, "alg": "mf", "eta": ETA0, "lambda": LAMBDA,
             "schedule": "parallel user-runs, atomic (red.add.v4.f32) item-row accumulation, bounded concurrency",
+            "epochs": "eta = eta0/epoch as in the reference (model.cc:36-38): warm-up steps are epochs 1..W, "
+                      "timed steps the epochs after them",
             "parallelism": "1 GPU" if n_gpus == 1 else "dsgd%d" % n_gpus,
             "l2": "inputs larger than L2: each epoch streams the rating tiles (8 B/rating) and all user rows"}
 
@@ -258,10 +264,11 @@ def run_b200_arm(args, wl):
     total_ms = ev[0].elapsed_time(ev[1])
     # the kernel's own duration, launch by launch (events recorded by the library around the
     # kernel on the same stream): a second, identical timed pass keeps the first one unperturbed
-    kern_ms = []
+    kern_ms, shapes = [], []
     for _ in range(args.steps):
         step_resident()
         kern_ms.append(c.last_kernel_ms())
+        shapes.append(c.last_launch())
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
     value = ntrain * args.steps / (total_ms * 1e-3)
@@ -313,10 +320,12 @@ def run_b200_arm(args, wl):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "kernel": "sgd_epoch_kernel<LPR=32,VPL=1,%s>" % args.schedule if k == 128 else "sgd_epoch_kernel",
+                     "kernel": KERNEL_NAMES.get(shapes[-1]["kernel"], "?"), "launch": shapes[-1],
                      "kernel_ms": kavg, "bytes_per_update": bytes_per_update(k), "updates_per_launch": ntrain,
-                     "note": "algorithmic bytes; theta rows stay in registers across a user-run and phi rows are "
-                             "served by L2, so DRAM traffic is far lower (see profiles/)"},
+                     "note": "algorithmic bytes (rating record + two factor rows read and written per update); "
+                             "theta rows stay in registers across a user-run and the item matrix (9.1 MB) lives in "
+                             "L2, so DRAM traffic is far lower and the fraction exceeds 1; the physical bound is "
+                             "the L2 atomic unit of the hottest slice (profiles/r1_sgd_stream.md)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / args.steps,
@@ -330,6 +339,13 @@ def run_b200_arm(args, wl):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries loaded later (NCCL prints its version
+    # banner to stdout when NCCL_DEBUG is set in the environment) must not be able to add to it:
+    # file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

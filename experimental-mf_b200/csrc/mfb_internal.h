@@ -102,8 +102,8 @@ struct Context {
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
   double rate_stream = 1.2e6, rate_burst = 3.5e6;  // updates/s per run in flight (measured; for the choice)
-  int opt_ring = 1;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose:
-                                // 1 when the staleness budget limits the launch, else 2)
+  int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the
+                                // deepest ring the budget of the hottest row leaves room for)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,
                                 // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t
   int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)

@@ -426,11 +426,17 @@ template <int LPR, int VPL>
 int launch_stream_r(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   int ring = c->opt_ring;
   if (ring == 0) {
-    // R = 2 hides the L2 latency with half the warps; when the staleness budget (not the hardware)
-    // limits the launch, R = 1 gets more updates per second out of the same budget
-    const void* k2 = stream_kernel<LPR, VPL, 2>(mode, a.nvec == LPR * VPL);
-    const int64_t cap = std::min<int64_t>(stream_capacity<LPR, VPL, 2>(c, k2), std::max((a.nruns - a.run_begin + LPR - 1) / LPR, 1));
-    ring = bounded_groups(c, cap, d->max_item_share, d->nruns, 2.0, a.eta) < cap ? 1 : 2;
+    // The bound on user-runs in flight does not depend on the ring depth, the budget of the hottest
+    // row does (R rows in flight per sub-warp).  Take the deepest ring (4, 2) that the row budget
+    // does not make narrower than the run bound / the hardware allows; otherwise R = 1, which gets
+    // the most updates per second out of a given row budget.
+    const int64_t spans = std::max((a.nruns - a.run_begin + LPR - 1) / LPR, 1);
+    const void* k1 = stream_kernel<LPR, VPL, 1>(mode, a.nvec == LPR * VPL);
+    const int64_t cap = std::min<int64_t>(stream_capacity<LPR, VPL, 1>(c, k1), spans);
+    const int64_t free_of_row = bounded_groups(c, cap, 0.0, d->nruns, 1.0, a.eta);  // run bound only
+    ring = 1;
+    if (bounded_groups(c, cap, d->max_item_share, d->nruns, 2.0, a.eta) >= free_of_row) ring = 2;
+    if (bounded_groups(c, cap, d->max_item_share, d->nruns, 4.0, a.eta) >= free_of_row) ring = 4;
   }
   switch (ring) {
     case 1: return launch_stream_t<LPR, VPL, 1>(c, d, a, mode);

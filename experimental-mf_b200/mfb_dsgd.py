@@ -136,6 +136,7 @@ def bench(args, wl, shape, rank, world, local, config):
     dist.all_reduce(h2d_t)
     sse, n = sse_host[-1]
     launches = w.ctx.launch_count() - launches0
+    shape = w.ctx.last_launch()
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = value * bytes_per_update(k) / 1e9 / world  # per GPU
@@ -144,7 +145,7 @@ def bench(args, wl, shape, rank, world, local, config):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": None, "peak_source": peak_src, "launch": shape,
                          "note": "per GPU, whole DSGD epoch (P cell kernels + P ring shifts), algorithmic bytes"},
             "cpu_baseline": None,
             "e2e": {"value": ntrain * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
