@@ -101,7 +101,7 @@ struct Context {
                                 // one record at a time; 2 = warp per run, 4 records batched; 4 = burst
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
-  double rate_stream = 1.2e6, rate_burst = 3.5e6;  // updates/s per run in flight (measured; for the choice)
+  double rate_stream = 1.2e6, rate_burst = 5.0e6;  // updates/s per run in flight (measured; for the choice)
   int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the
                                 // deepest ring the budget of the hottest row leaves room for)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,

@@ -21,6 +21,7 @@
 //    the NEXT one (measured: 2k cycles per batch of four).
 //  * a warp walks a span of 32 consecutive runs: lane l keeps the user id and end of run l.
 #include <algorithm>
+#include <type_traits>
 
 #include "mfb_internal.h"
 #include "mfb_sgd_args.cuh"
@@ -86,13 +87,16 @@ struct BurstSmem {
   static constexpr int WARP_BYTES = ROWS + BIAS + CHUNK + PFT;
 };
 
-template <int B, int MODE>
+// EXACT: rows of exactly 32 float4 (k = 128): no lane predicates.
+template <int B, int MODE, bool EXACT>
 __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const int nspans) {
   using SM = BurstSmem<B>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const bool lane_ok = lane < a.nvec;
+  const bool lane_ok = EXACT || lane < a.nvec;
+  const float eta = a.eta, lameta = a.lameta, lm1 = a.lm1, gb = a.gb;
+  const int nvec = EXACT ? 32 : a.nvec;
   const float4* __restrict__ phi4 = reinterpret_cast<const float4*>(a.phi);
   float4* theta4 = reinterpret_cast<float4*>(a.theta);
   const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + (threadIdx.x >> 5) * SM::WARP_BYTES;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       if (nri < span_n) {
         n_uid = __shfl_sync(FULL, s_uid, nri);
         if (n_uid != uid) {  // (the same user again continues in registers)
-          if (lane_ok) cp_async16(pft_me, theta4 + (int64_t)n_uid * a.nvec + lane);
+          if (lane_ok) cp_async16(pft_me, theta4 + (int64_t)n_uid * nvec + lane);
           if (lane == 0) cp_async16(pfb, a.bu + (n_uid & ~3));
           pf_iter = iter;
         }
@@ -164,16 +168,18 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     __syncwarp();
 
     // request the rows and bias quads of the batch [j0, j0+n) into slot p; ids/ratings -> registers
+    // Branch-free: a batch never crosses the 32-record chunk, so records idx .. idx+n-1 are in the
+    // buffer; slots b >= n are filled with the batch's last row again (never used).
     auto request = [&](int p, int j0, int n, int (&vv)[B], float (&rr)[B]) {
+      const uint32_t cb = chunk0 + cbuf * 256 + ((j0 - cbase) & 31) * 4;
+      const bool lane0 = lane == 0;
 #pragma unroll
       for (int b = 0; b < B; b++) {
-        const int idx = (j0 - cbase + b) & 31;
-        vv[b] = lds1i(chunk0 + cbuf * 256 + idx * 4);
-        rr[b] = lds1(chunk0 + cbuf * 256 + 128 + idx * 4);
-        if (b < n) {
-          if (lane_ok) cp_async16(rows_me + (p * B + b) * 512, phi4 + (int64_t)vv[b] * a.nvec + lane);
-          if (lane == 0) cp_async16(bias0 + (p * B + b) * 16, a.bv + (vv[b] & ~3));
-        }
+        const uint32_t at = cb + min(b, n - 1) * 4;
+        vv[b] = lds1i(at);
+        rr[b] = lds1(at + 128);
+        if (lane_ok) cp_async16(rows_me + (p * B + b) * 512, phi4 + (int64_t)vv[b] * nvec + lane);
+        if (lane0) cp_async16(bias0 + (p * B + b) * 16, a.bv + (vv[b] & ~3));
       }
     };
 
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       // ---- run switch: the batch about to be computed opens run nri ----------------------------------
       if (cur_new_run) {
         if (ri >= 0) {
-          if (lane_ok) __stcg(theta4 + (int64_t)uid * a.nvec + lane, t);
+          if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
           if (lane == 0) __stcg(a.bu + uid, bu);
         }
         if (n_uid != uid) {
@@ -227,57 +233,67 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       cp_async_wait<1>();  // everything but the requests just made has landed
       __syncwarp();
 
-      // ---- this batch: all inner products at once ---------------------------------------------------
-      float4 f[B];
-      float bvv[B];
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        f[b] = lds4(rows_me + (p * B + b) * 512);
-        bvv[b] = lds1(bias0 + (p * B + b) * 16 + (v[b] & 3) * 4);
-      }
-      float D[B], G[B][B];
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        D[b] = dot4(t, f[b]);
-#pragma unroll
-        for (int c = b + 1; c < B; c++) G[b][c] = dot4(f[b], f[c]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      // ---- this batch: all inner products at once, residuals by recurrence, row updates ---------------
+      auto compute = [&](auto full_tag) {
+        constexpr bool FULLB = decltype(full_tag)::value;  // all B records present: no per-record tests
+        float4 f[B];
+        float bvv[B];
 #pragma unroll
         for (int b = 0; b < B; b++) {
-          D[b] += __shfl_xor_sync(FULL, D[b], o);
-#pragma unroll
-          for (int c = b + 1; c < B; c++) G[b][c] += __shfl_xor_sync(FULL, G[b][c], o);
+          f[b] = lds4(rows_me + (p * B + b) * 512);
+          bvv[b] = lds1(bias0 + (p * B + b) * 16 + (v[b] & 3) * 4);
         }
-      }
-      // ---- residuals by recurrence, row updates ------------------------------------------------------
-      float coef[B];
-      float tpow = 1.0f;
+        float D[B], G[B][B];
 #pragma unroll
-      for (int b = 0; b < B; b++) {
-        if (b < nb) {
-          float d = tpow * D[b];
+        for (int b = 0; b < B; b++) {
+          D[b] = dot4(t, f[b]);
 #pragma unroll
-          for (int c = 0; c < b; c++) d = fmaf(coef[c], G[c][b], d);
-          const float e = a.eta * (((r[b] - bvv[b] - a.gb) - d) - bu);
-          float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)v[b] * a.nvec + lane;
-          if (MODE == MFB_MODE_ATOMIC) {  // increment of phi_b, from theta BEFORE this record
-            const float4 nf = axpby4(e, t, a.lm1, f[b]);
-            if (lane_ok) burst_red4(dst, nf);
-          } else {
-            const float4 nf = axpby4(e, t, a.lameta, f[b]);
-            if (lane_ok) __stcg(dst, nf);
+          for (int c = b + 1; c < B; c++) G[b][c] = dot4(f[b], f[c]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int b = 0; b < B; b++) {
+            D[b] += __shfl_xor_sync(FULL, D[b], o);
+#pragma unroll
+            for (int c = b + 1; c < B; c++) G[b][c] += __shfl_xor_sync(FULL, G[b][c], o);
           }
-          if (lane == 0) burst_red1(a.bv + v[b], fmaf(a.lm1, bvv[b], e));
-          t = axpby4(e, f[b], a.lameta, t);
-          bu = fmaf(a.lameta, bu, e);
-#pragma unroll
-          for (int c = 0; c < b; c++) coef[c] *= a.lameta;
-          coef[b] = e;
-          tpow *= a.lameta;
         }
-      }
+        float coef[B];
+        float tpow = 1.0f;
+        float my_bias = 0.f;  // lane b carries the bias increment of record b
+        int my_v = 0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+          if (FULLB || b < nb) {
+            float d = tpow * D[b];
+#pragma unroll
+            for (int c = 0; c < b; c++) d = fmaf(coef[c], G[c][b], d);
+            const float e = eta * (((r[b] - bvv[b] - gb) - d) - bu);
+            float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)v[b] * nvec + lane;
+            if (MODE == MFB_MODE_ATOMIC) {  // increment of phi_b, from theta BEFORE this record
+              const float4 nf = axpby4(e, t, lm1, f[b]);
+              if (lane_ok) burst_red4(dst, nf);
+            } else {
+              const float4 nf = axpby4(e, t, lameta, f[b]);
+              if (lane_ok) __stcg(dst, nf);
+            }
+            if (lane == b) {
+              my_bias = fmaf(lm1, bvv[b], e);
+              my_v = v[b];
+            }
+            t = axpby4(e, f[b], lameta, t);
+            bu = fmaf(lameta, bu, e);
+#pragma unroll
+            for (int c = 0; c < b; c++) coef[c] *= lameta;
+            coef[b] = e;
+            tpow *= lameta;
+          }
+        }
+        if (lane < (FULLB ? B : nb)) burst_red1(a.bv + my_v, my_bias);
+      };
+      if (nb == B) compute(std::true_type{});
+      else compute(std::false_type{});
 
       if (!more) break;
       j = j1;
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       }
     }
     // last run of the span
-    if (lane_ok) __stcg(theta4 + (int64_t)uid * a.nvec + lane, t);
+    if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
     if (lane == 0) __stcg(a.bu + uid, bu);
     cp_async_wait<0>();  // nothing of this span may land in the buffers of the next one
     __syncwarp();
@@ -303,8 +319,12 @@ namespace {
 
 template <int B>
 int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
-  const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC>
-                                          : (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD>;
+  const bool exact = a.nvec == 32;
+  const void* k = mode == MFB_MODE_ATOMIC
+                      ? (exact ? (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC, true>
+                               : (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC, false>)
+                      : (exact ? (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, true>
+                               : (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, false>);
   const int nruns = a.nruns - a.run_begin;
   const int nspans = (nruns + 31) / 32;
   int per_sm = 0;
