@@ -121,6 +121,49 @@ int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bou
   return MFB_OK;
 }
 
+// One run per user: the user's runs concatenated in file order, users in the order of their first
+// run, `users_per_block` runs per Block.  (A DSGD cell holds, for each user, the pieces of `split`
+// runs of the source file; merging them restores the length of the user's burst of updates.)
+int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out) {
+  MFB_REQUIRE(b && out && users_per_block >= 1, "bad argument");
+  const Dataset& d = b->d;
+  const int64_t nruns = (int64_t)d.h_run_uid.size();
+  int32_t maxu = -1;
+  for (int32_t u : d.h_run_uid) maxu = std::max(maxu, u);
+  std::vector<int64_t> count((size_t)maxu + 2, 0);
+  std::vector<int32_t> order;  // users by first appearance
+  for (int64_t r = 0; r < nruns; r++) {
+    const int32_t u = d.h_run_uid[r];
+    if (count[u] == 0 && d.h_run_off[r + 1] > d.h_run_off[r]) order.push_back(u);
+    count[u] += d.h_run_off[r + 1] - d.h_run_off[r];
+  }
+  std::vector<int64_t> slot((size_t)maxu + 2, -1), fill((size_t)maxu + 2, 0);
+  mfb_blocks* o = blocks_new();  // run_off = block_off = {0}
+  Dataset& m = o->d;
+  int64_t total = 0;
+  for (size_t i = 0; i < order.size(); i++) {
+    const int32_t u = order[i];
+    slot[u] = total;
+    total += count[u];
+    m.h_run_uid.push_back(u);
+    m.h_run_off.push_back((int32_t)total);
+    if ((i + 1) % (size_t)users_per_block == 0) m.h_block_off.push_back((int64_t)m.h_run_uid.size());
+  }
+  if (m.h_block_off.back() != (int64_t)m.h_run_uid.size()) m.h_block_off.push_back((int64_t)m.h_run_uid.size());
+  m.h_vid.resize(total);
+  m.h_rating.resize(total);
+  for (int64_t r = 0; r < nruns; r++) {
+    const int32_t u = d.h_run_uid[r];
+    for (int32_t t = d.h_run_off[r]; t < d.h_run_off[r + 1]; t++) {
+      const int64_t at = slot[u] + fill[u]++;
+      m.h_vid[at] = d.h_vid[t];
+      m.h_rating[at] = d.h_rating[t];
+    }
+  }
+  *out = o;
+  return MFB_OK;
+}
+
 void mfb_blocks_free(mfb_blocks* b) { delete b; }
 int64_t mfb_blocks_num_blocks(const mfb_blocks* b) { return b ? (int64_t)b->d.h_block_off.size() - 1 : -1; }
 int64_t mfb_blocks_num_runs(const mfb_blocks* b) { return b ? (int64_t)b->d.h_run_uid.size() : -1; }

@@ -227,6 +227,12 @@ void mfb_destroy(mfb_ctx* h) {
   cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->d_stage_vid[b]);
+    cudaFree(c->d_stage_code[b]);
+    if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
+  }
+  cudaFree(c->d_dict);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   delete h;
 }
@@ -274,6 +280,8 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "ring")) {
     MFB_REQUIRE(value >= 0 && value <= 4, "ring must be 0..4");
     c->opt_ring = value;
+  } else if (!strcmp(name, "packed_h2d")) {
+    c->opt_packed_h2d = value != 0;
   } else if (!strcmp(name, "throttle")) {
     c->opt_throttle = value != 0;
   } else if (!strcmp(name, "eta_scaling")) {
@@ -541,6 +549,9 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_CUDA(cudaSetDevice(c->device));
   if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   if (chunk_ratings <= 0) chunk_ratings = 8 << 20;
+  // chunks grow geometrically (x1, x2, x4, x8 the given size, then constant): the first kernel starts
+  // after a small copy, and there are few launches (each has a ramp and a tail)
+  const int64_t max_chunk = chunk_ratings * 8;
   begin_timing(c);
   // the copy stream must not overwrite tiles that work queued earlier on the main stream still reads
   cudaEvent_t start_ev;
@@ -552,22 +563,54 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   start_ev = c->chunk_events[0];
   MFB_CUDA(cudaEventRecord(start_ev, c->stream));
   MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, start_ev, 0));
+  const bool packed = s->packed && c->opt_packed_h2d;
+  if (packed) {
+    if (c->stage_capacity < max_chunk + 65536) {
+      MFB_CUDA(cudaStreamSynchronize(c->stream));
+      MFB_CUDA(cudaStreamSynchronize(c->copy_stream));
+      c->stage_capacity = max_chunk + 65536;
+      for (int b = 0; b < 2; b++) {
+        cudaFree(c->d_stage_vid[b]);
+        cudaFree(c->d_stage_code[b]);
+        MFB_CUDA(cudaMalloc(&c->d_stage_vid[b], c->stage_capacity * sizeof(uint16_t)));
+        MFB_CUDA(cudaMalloc(&c->d_stage_code[b], c->stage_capacity));
+        if (!c->stage_free[b]) MFB_CUDA(cudaEventCreateWithFlags(&c->stage_free[b], cudaEventDisableTiming));
+      }
+      if (!c->d_dict) MFB_CUDA(cudaMalloc(&c->d_dict, 256 * sizeof(float)));
+    }
+    MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    for (int b = 0; b < 2; b++) MFB_CUDA(cudaEventRecord(c->stage_free[b], c->stream));
+  }
   int64_t r0 = 0;
   size_t chunk = 0;
   while (r0 < d->nruns) {
     int64_t r1 = r0;
     const int64_t o0 = s->h_run_off[r0];
-    while (r1 < d->nruns && s->h_run_off[r1 + 1] - o0 <= chunk_ratings) r1++;
+    const int64_t want = std::min(max_chunk, chunk_ratings << std::min<size_t>(chunk, 3));
+    {  // last run whose end is within `want` records (run_off is sorted)
+      const int32_t* ro = s->h_run_off.data();
+      r1 = std::upper_bound(ro + r0 + 1, ro + d->nruns + 1, (int32_t)std::min<int64_t>(o0 + want, INT32_MAX)) - ro - 1;
+    }
     if (r1 == r0) r1 = r0 + 1;  // a single run longer than the chunk size
     const int64_t o1 = s->h_run_off[r1];
+    const bool staged = packed && o1 - o0 <= c->stage_capacity;
+    const int sb = (int)(chunk & 1);
     MFB_CUDA(cudaMemcpyAsync(d->d_run_uid + r0, s->h_run_uid.data() + r0, (r1 - r0) * sizeof(int32_t),
                              cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(d->d_run_off + r0, s->h_run_off.data() + r0, (r1 - r0 + 1) * sizeof(int32_t),
                              cudaMemcpyHostToDevice, c->copy_stream));
-    MFB_CUDA(cudaMemcpyAsync(d->d_vid + o0, s->h_vid.data() + o0, (o1 - o0) * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, c->copy_stream));
-    MFB_CUDA(cudaMemcpyAsync(d->d_rating + o0, s->h_rating.data() + o0, (o1 - o0) * sizeof(float),
-                             cudaMemcpyHostToDevice, c->copy_stream));
+    if (staged) {  // 3 bytes per record into the staging buffer, expanded on the device
+      MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->stage_free[sb], 0));
+      MFB_CUDA(cudaMemcpyAsync(c->d_stage_vid[sb], s->p_vid.data() + o0, (o1 - o0) * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+      MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code.data() + o0, (o1 - o0), cudaMemcpyHostToDevice,
+                               c->copy_stream));
+    } else {
+      MFB_CUDA(cudaMemcpyAsync(d->d_vid + o0, s->h_vid.data() + o0, (o1 - o0) * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+      MFB_CUDA(cudaMemcpyAsync(d->d_rating + o0, s->h_rating.data() + o0, (o1 - o0) * sizeof(float),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    }
     ++chunk;
     if (c->chunk_events.size() <= chunk) {
       cudaEvent_t e;
@@ -576,6 +619,15 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
     }
     MFB_CUDA(cudaEventRecord(c->chunk_events[chunk], c->copy_stream));
     MFB_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_events[chunk], 0));
+    if (staged) {
+      int rc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid + o0, d->d_rating + o0, o1 - o0);
+      if (rc) return rc;
+      MFB_CUDA(cudaEventRecord(c->stage_free[sb], c->stream));
+      c->h2d_bytes += (o1 - o0) * 3;
+    } else {
+      c->h2d_bytes += (o1 - o0) * 8;
+    }
+    c->h2d_bytes += (r1 - r0) * 8 + 4;
     int rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
     if (rc) return rc;
     r0 = r1;
@@ -627,6 +679,47 @@ int mfb_blocks_pin(mfb_blocks* b) {
   MFB_CUDA(reg(s->h_vid.data(), s->h_vid.size() * sizeof(int32_t)));
   MFB_CUDA(reg(s->h_rating.data(), s->h_rating.size() * sizeof(float)));
   s->pinned = true;
+  // compact form for streaming: u16 item ids + u8 codes into a table of the distinct rating values
+  s->packed = false;
+  const size_t n = s->h_vid.size();
+  bool fits = n > 0;
+  for (size_t i = 0; fits && i < n; i++) fits = s->h_vid[i] >= 0 && s->h_vid[i] < 65536;
+  if (fits) {
+    std::vector<uint8_t> code(n);
+    int ndict = 0;
+    uint32_t last_bits = 0;
+    int last_code = -1;
+    for (size_t i = 0; fits && i < n; i++) {
+      uint32_t bits;
+      memcpy(&bits, &s->h_rating[i], 4);
+      if (last_code < 0 || bits != last_bits) {
+        int k = 0;
+        for (; k < ndict; k++) {
+          uint32_t db;
+          memcpy(&db, &s->p_dict[k], 4);
+          if (db == bits) break;
+        }
+        if (k == ndict) {
+          if (ndict == 256) {
+            fits = false;
+            break;
+          }
+          s->p_dict[ndict++] = s->h_rating[i];
+        }
+        last_bits = bits;
+        last_code = k;
+      }
+      code[i] = (uint8_t)last_code;
+    }
+    if (fits) {
+      s->p_vid.resize(n);
+      for (size_t i = 0; i < n; i++) s->p_vid[i] = (uint16_t)s->h_vid[i];
+      s->p_code.swap(code);
+      MFB_CUDA(reg(s->p_vid.data(), n * sizeof(uint16_t)));
+      MFB_CUDA(reg(s->p_code.data(), n));
+      s->packed = true;
+    }
+  }
   return MFB_OK;
 }
 
@@ -638,6 +731,13 @@ int mfb_blocks_unpin(mfb_blocks* b) {
   if (!s->h_run_off.empty()) cudaHostUnregister(s->h_run_off.data());
   if (!s->h_vid.empty()) cudaHostUnregister(s->h_vid.data());
   if (!s->h_rating.empty()) cudaHostUnregister(s->h_rating.data());
+  if (s->packed) {
+    cudaHostUnregister(s->p_vid.data());
+    cudaHostUnregister(s->p_code.data());
+    std::vector<uint16_t>().swap(s->p_vid);
+    std::vector<uint8_t>().swap(s->p_code);
+    s->packed = false;
+  }
   s->pinned = false;
   return MFB_OK;
 }
@@ -902,6 +1002,7 @@ float mfb_last_kernel_ms(mfb_ctx* h) {
 }
 
 int64_t mfb_launch_count(mfb_ctx* h) { return h ? h->c.launches : 0; }
+int64_t mfb_h2d_bytes(mfb_ctx* h) { return h ? h->c.h2d_bytes : 0; }
 
 int mfb_last_launch(mfb_ctx* h, int out[4]) {
   MFB_REQUIRE(h && out, "NULL argument");

@@ -44,6 +44,13 @@ struct Dataset {
   std::vector<float> h_rating;
   std::vector<int64_t> h_block_off; // [nblocks+1] first run of each block
   bool pinned = false;              // host arrays registered with cudaHostRegister
+  // compact wire form of vid/rating for host -> device streaming (mfb_blocks_pin builds it when the
+  // data allow: item ids below 65536 and at most 256 distinct rating values): 3 bytes per record
+  // instead of 8, lossless
+  std::vector<uint16_t> p_vid;
+  std::vector<uint8_t> p_code;
+  float p_dict[256] = {0};
+  bool packed = false;
   // device SoA tiles
   int64_t nruns = 0, nratings = 0, nblocks = 0;
   int32_t* d_run_uid = nullptr;
@@ -77,8 +84,15 @@ struct Context {
   // host-streamed epochs: a second stream carries the H2D copies of the next chunk
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
+  // ... packed chunks land in one of two staging buffers and are expanded on the device
+  uint16_t* d_stage_vid[2] = {nullptr, nullptr};
+  uint8_t* d_stage_code[2] = {nullptr, nullptr};
+  float* d_dict = nullptr;  // [256]
+  int64_t stage_capacity = 0;
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
   bool timed = false;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0;  // bytes copied host -> device by the streamed epochs since create
   // dpmf: optional emulation of the reference's noise_ table (ordered parity mode only)
   float* d_noise_table = nullptr;
   int64_t noise_table_size = 0;
@@ -106,6 +120,7 @@ struct Context {
                                 // deepest ring the budget of the hottest row leaves room for)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,
                                 // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t
+  int opt_packed_h2d = 1;       // streamed epochs send the compact 3-byte records when the blocks have them
   int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)
   int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
   int last_grid = 0, last_threads = 0, last_ring = 0;  // launch shape of the most recent epoch kernel
@@ -143,6 +158,9 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
                int64_t run_begin, int64_t run_end);
 int launch_sse(Context* c, Dataset* d, float gb);
 int launch_fill_normal(Context* c, uint64_t seed, float scale);
+// expand n packed records (u16 item id, u8 rating code) into the SoA tiles
+int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* code, const float* dict, int32_t* vid,
+                  float* rating, int64_t n);
 // kernels (mfb_sgld.cu)
 int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int mode);
 int launch_flush(Context* c, Dataset* d, const mfb_sgld_params* p);

@@ -389,6 +389,29 @@ __global__ void fill_normal_kernel(float* p, int64_t rows, int cols, int stride,
   }
 }
 
+// expand packed records (the compact host form, mfb_blocks_pin): 3 B in, 8 B out per record
+__global__ void unpack_kernel(const uint16_t* __restrict__ vid16, const uint8_t* __restrict__ code,
+                              const float* __restrict__ dict, int32_t* __restrict__ vid,
+                              float* __restrict__ rating, int64_t n) {
+  __shared__ float sdict[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sdict[i] = dict[i];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    vid[i] = vid16[i];
+    rating[i] = sdict[code[i]];
+  }
+}
+
+int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* code, const float* dict, int32_t* vid,
+                  float* rating, int64_t n) {
+  if (n <= 0) return MFB_OK;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+  unpack_kernel<<<grid, 256, 0, c->stream>>>(vid16, code, dict, vid, rating, n);
+  MFB_CUDA(cudaGetLastError());
+  c->launches++;
+  return MFB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 namespace {
 
@@ -452,6 +475,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.vid = d->d_vid;
   a.rating = d->d_rating;
   a.counter = c->d_counter;
+  a.big_spans = 0;
   a.run_begin = (int)run_begin;
   a.nruns = (int)run_end;
   a.nvec = c->stride / 4;

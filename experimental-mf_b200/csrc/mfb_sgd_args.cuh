@@ -17,6 +17,9 @@ struct SgdArgs {
   const float* rating;
   int* counter;
   int run_begin, nruns, nvec;  // runs [run_begin, nruns) are processed
+  // stream/burst kernels: the first big_spans spans are full (LPR resp. 32 consecutive runs), the runs
+  // after them are handed out one by one, so that the kernel's tail is one run long, not one span
+  int big_spans;
   float eta, lameta, lm1, gb;
   int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
   int throttle;  // streaming kernel: wait for the previous record's bias atomic before the next reductions

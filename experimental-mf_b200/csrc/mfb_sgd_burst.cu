@@ -118,8 +118,11 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     if (lane == 0) sp = atomicAdd(a.counter, 1);
     sp = __shfl_sync(FULL, sp, 0);
     if (sp >= nspans) break;
-    const int run0 = a.run_begin + sp * 32;
-    const int span_n = min(32, a.nruns - run0);
+    int run0 = a.run_begin + sp * 32, span_n = 32;
+    if (sp >= a.big_spans) {  // the tail of the launch: single runs
+      run0 = a.run_begin + a.big_spans * 32 + (sp - a.big_spans);
+      span_n = 1;
+    }
     int s_uid = 0, s_end = 0;
     if (lane < span_n) {
       s_uid = __ldg(a.run_uid + run0 + lane);
@@ -326,15 +329,17 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
                       : (exact ? (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, true>
                                : (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, false>);
   const int nruns = a.nruns - a.run_begin;
-  const int nspans = (nruns + 31) / 32;
   int per_sm = 0;
   constexpr int WARP_BYTES = BurstSmem<B>::WARP_BYTES;
   MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * WARP_BYTES));
   per_sm = std::max(per_sm, 1);
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-  int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max(nspans, 1));
+  int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max((nruns + 31) / 32, 1));
   // a run holds the current batch and the requested one: 2B item rows between gather and reduction
   warps = bounded_groups(c, warps, d->max_item_share, d->nruns, 2.0 * B, a.eta);
+  SgdArgs aa = a;
+  aa.big_spans = (int)std::max<int64_t>(0, (nruns - 2 * warps) / 32);  // ~2 single runs per warp at the end
+  const int nspans = aa.big_spans + (nruns - aa.big_spans * 32);
   int grid, threads;
   if (warps <= c->sm_count) {
     grid = (int)warps;
@@ -348,7 +353,7 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   c->last_grid = grid;
   c->last_threads = threads;
   c->last_ring = B;
-  void* args[] = {(void*)&a, (void*)&nspans};
+  void* args[] = {(void*)&aa, (void*)&nspans};
   MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
   MFB_CUDA(cudaGetLastError());
   c->launches++;

@@ -200,8 +200,12 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
       if (sp >= nspans) {
         done = true;
       } else {
-        const int run0 = a.run_begin + sp * LPR;
-        span_n = min(LPR, a.nruns - run0);
+        int run0 = a.run_begin + sp * LPR;
+        span_n = LPR;
+        if (sp >= a.big_spans) {  // the tail of the launch: single runs
+          run0 = a.run_begin + a.big_spans * LPR + (sp - a.big_spans);
+          span_n = 1;
+        }
         s_uid = 0;
         s_end = 0;
         if (gl < span_n) {
@@ -395,11 +399,13 @@ template <int LPR, int VPL, int R>
 int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   const void* k = stream_kernel<LPR, VPL, R>(mode, a.nvec == LPR * VPL);
   const int nruns = a.nruns - a.run_begin;
-  const int nspans = (nruns + LPR - 1) / LPR;
   const int subs_per_warp = 32 / LPR;
   constexpr int WARP_BYTES = StreamSmem<LPR, VPL, R>::WARP_BYTES;
-  int64_t subs = std::min<int64_t>(stream_capacity<LPR, VPL, R>(c, k), std::max(nspans, 1));
+  int64_t subs = std::min<int64_t>(stream_capacity<LPR, VPL, R>(c, k), std::max((nruns + LPR - 1) / LPR, 1));
   subs = bounded_groups(c, subs, d->max_item_share, d->nruns, ring_weight<R>(), a.eta);
+  SgdArgs aa = a;
+  aa.big_spans = (int)std::max<int64_t>(0, (nruns - 2 * subs) / LPR);  // ~2 single runs per sub-warp at the end
+  const int nspans = aa.big_spans + (nruns - aa.big_spans * LPR);
   // spread the warps over all SMs before stacking them: 1..4 warps per CTA
   const int64_t warps = (subs + subs_per_warp - 1) / subs_per_warp;
   int grid, threads;
@@ -415,7 +421,7 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   c->last_grid = grid;
   c->last_threads = threads;
   c->last_ring = R;
-  void* args[] = {(void*)&a, (void*)&nspans};
+  void* args[] = {(void*)&aa, (void*)&nspans};
   MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
   MFB_CUDA(cudaGetLastError());
   c->launches++;

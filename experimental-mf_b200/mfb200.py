@@ -81,6 +81,7 @@ SIGNATURES = {
     "mfb_admf_get_lams": (C.c_int, [C.c_void_p, f32p]),
     "mfb_admf_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]),
     "mfb_blocks_split_by_item": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p)]),
+    "mfb_blocks_merge_runs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "mfb_probe_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "mfb_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "mfb_launch_count": (C.c_int64, [C.c_void_p]),
+    "mfb_h2d_bytes": (C.c_int64, [C.c_void_p]),
     "mfb_last_launch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
 }
 
@@ -194,6 +196,11 @@ class Blocks:
         out = (C.c_void_p * n)()
         _check(lib().mfb_blocks_split_by_item(self.h, n, b.ctypes.data_as(i32p), out))
         return [Blocks(C.c_void_p(x)) for x in out]
+
+    def merge_runs(self, users_per_block=500):
+        out = C.c_void_p()
+        _check(lib().mfb_blocks_merge_runs(self.h, users_per_block, C.byref(out)))
+        return Blocks(out)
 
     @property
     def nblocks(self):
@@ -462,6 +469,9 @@ class Context:
 
     def launch_count(self):
         return lib().mfb_launch_count(self.h)
+
+    def h2d_bytes(self):
+        return lib().mfb_h2d_bytes(self.h)
 
     def last_launch(self):
         out = (C.c_int * 4)()

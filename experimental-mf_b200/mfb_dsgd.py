@@ -32,12 +32,21 @@ def dsgd_schedule(rank, world):
 class DsgdWorker:
     """This rank's shard of the model and data on its GPU, plus the NCCL ring."""
 
-    def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200):
+    def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200, merge=False):
         self.rank, self.world, self.nv = rank, world, nv
         self.bounds = item_bounds(nv, world)
         self.ctx = mb.Context(nu, nv, k, device)
         self.ctx.init_normal(seed, 1e-2)  # counter-based: identical on every rank
         self.cells = train.split_by_item(self.bounds)
+        if merge:
+            # one run per user and cell: the cell cuts every run of the file into `world` pieces and
+            # the file itself holds `split` runs per user; merged, the user's burst of consecutive
+            # updates has length (ratings of the user) / world instead of / (world * split).
+            # The bound on runs in flight stays the same absolute number of runs.
+            before = sum(b.nruns for b in self.cells)
+            self.cells = [b.merge_runs() for b in self.cells]
+            after = max(1, sum(b.nruns for b in self.cells))
+            self.ctx.set_option("run_fraction_ppm", int(3500 * before / after))
         self.cell_ds = [self.ctx.dataset_from_blocks(b) for b in self.cells]
         self.test_ds = self.ctx.dataset_from_blocks(test)
         self.ntrain = sum(b.nratings for b in self.cells)
@@ -78,7 +87,7 @@ def bench(args, wl, shape, rank, world, local, config):
     t0 = time.time()
     tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=test_frac, user_begin=u0, user_end=u1))
     gen_s = time.time() - t0
-    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, unique_id)
+    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, unique_id, merge=bool(int(os.environ.get("MFB_DSGD_MERGE", "0"))))
     stream = torch.cuda.current_stream()
     w.ctx.set_stream(stream.cuda_stream)
     mode = {"hogwild": mb.MODE_HOGWILD, "atomic": mb.MODE_ATOMIC}[args.schedule]

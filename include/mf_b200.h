@@ -172,6 +172,9 @@ int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float e
 /* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
  * the next epoch kernel on `ds` waits for the copy.  Used by the multi-GPU end-to-end path. */
 int mfb_dataset_refresh_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src);
+/* pin: registers the arrays with CUDA and, when the data allow (item ids < 65536, at most 256 distinct
+ * rating values), builds a lossless compact copy (u16 id + u8 code, 3 bytes per record) that the
+ * streamed epoch sends instead of the 8-byte records and expands on the device */
 int mfb_blocks_pin(mfb_blocks* b);
 int mfb_blocks_unpin(mfb_blocks* b);
 /* MF::calc_mse (model.cc:41-73): SUM of squared errors and the record count. */
@@ -230,6 +233,8 @@ int mfb_admf_epoch(mfb_ctx* ctx, int ds, float eta, float eta_reg, int loss, flo
  * The unique id is created on rank 0 and distributed by the host program (bench.py uses
  * torch.distributed for that plumbing). */
 int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bounds, mfb_blocks** out);
+/* one run per user (its runs concatenated in file order, users in order of first appearance) */
+int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out);
 int mfb_comm_unique_id(void* out128);
 int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
 int mfb_comm_destroy(mfb_ctx* ctx);
@@ -252,6 +257,8 @@ int mfb_probe_read(mfb_ctx* ctx, uint64_t out[4]);
  * context's stream; valid after mfb_sync) and the number of kernel launches since create */
 float mfb_last_kernel_ms(mfb_ctx* ctx);
 int64_t mfb_launch_count(mfb_ctx* ctx);
+/* bytes copied host -> device by mfb_sgd_epoch_from_host since the context was created */
+int64_t mfb_h2d_bytes(mfb_ctx* ctx);
 /* shape of the most recent SGD epoch launch: out = {kernel variant, grid, threads per CTA, ring depth} */
 int mfb_last_launch(mfb_ctx* ctx, int out[4]);
 

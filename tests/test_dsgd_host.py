@@ -51,6 +51,28 @@ def test_split_by_item_partitions_every_record():
     np.testing.assert_array_equal(p0.rating, tr.rating[m])
 
 
+def test_merge_runs_keeps_every_record_and_file_order_within_a_user():
+    nu, nv = 400, 90
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 20000, test_frac=0.0, users_per_block=50))
+    cell = tr.split_by_item(np.array([0, 45, 90], np.int32))[1]
+    m = cell.merge_runs(users_per_block=64)
+    assert m.nratings == cell.nratings and len(m.run_off) == m.nruns + 1
+    assert m.run_off[0] == 0 and m.run_off[-1] == m.nratings and np.all(np.diff(m.run_off) > 0)
+    assert len(np.unique(m.run_uid)) == m.nruns == len(np.unique(cell.run_uid))
+    assert list(m.block_off) == list(range(0, m.nruns, 64)) + [m.nruns]
+    # users in order of first appearance; each user's records in file order
+    first = {}
+    for r, u in enumerate(cell.run_uid):
+        first.setdefault(int(u), r)
+    assert list(m.run_uid) == sorted(first, key=first.get)
+    cu = np.repeat(cell.run_uid, np.diff(cell.run_off))
+    for r in (0, 1, m.nruns // 2, m.nruns - 1):
+        u = m.run_uid[r]
+        lo, hi = m.run_off[r], m.run_off[r + 1]
+        np.testing.assert_array_equal(m.vid[lo:hi], cell.vid[cu == u])
+        np.testing.assert_array_equal(m.rating[lo:hi], cell.rating[cu == u])
+
+
 def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib):
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
