@@ -230,7 +230,9 @@ int launch_admf_t(Context* c, const Dataset* d, const AdmfArgs& a, int mode) {
     admf_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED><<<1, 32, 0, c->stream>>>(a);
   } else {
     auto k = admf_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC>;
-    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns);
+    // The regularisers are learned from the same stale rows, which makes this path less tolerant than
+    // plain SGD (measured: NaN at 6 times this width at eta = 0.02); the step of a stale update is eta.
+    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, 6, a.eta);
     k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   }
   MFB_CUDA(cudaGetLastError());

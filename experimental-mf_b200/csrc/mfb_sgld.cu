@@ -336,7 +336,9 @@ int launch_sgld_t(Context* c, const Dataset* d, const SgldArgs& a, int mode) {
     sgld_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED><<<1, 32, 0, c->stream>>>(a);
   } else {
     auto k = sgld_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD>;
-    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns);
+    // one record between gather and write-back per group; the step of a stale update is
+    // scal = eta*ntrain*bound*lambda_r (dpmf.h:46), the counterpart of plain SGD's eta
+    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, 1, a.scal);
     k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   }
   MFB_CUDA(cudaGetLastError());
