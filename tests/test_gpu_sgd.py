@@ -262,3 +262,61 @@ def test_streamed_epoch_from_host_equals_resident_epoch(packed, fractional):
     blocks.unpin()
     c1.close()
     c2.close()
+
+
+def test_staleness_probe_counts_every_update_and_sees_no_staleness_when_serial():
+    """mfb_probe_*: with one run in flight every update sees all earlier updates of its item
+    (staleness 0); with the whole machine in flight on a file with one very hot item it does not."""
+    nu, nv, dim = 4000, 300, 128
+    rng = np.random.default_rng(5)
+    lens = rng.integers(5, 40, nu)
+    n = int(lens.sum())
+    run_off = np.r_[0, np.cumsum(lens)]
+    vid = np.concatenate([np.r_[0, 1 + rng.permutation(nv - 1)[:l - 1]] for l in lens]).astype(np.int32)  # item 0 in every run
+    ds = ol.Dataset(np.r_[np.arange(0, nu, 500), nu], rng.permutation(nu), run_off, vid, rng.integers(1, 6, n))
+    m = ol.Model(nu, nv, dim, seed=2, scale=0.1)
+    for groups, kernel in ((1, 3), (1, 4), (0, 3), (0, 4)):
+        c = ctx_from_model(m)
+        c.set_option("row_concurrency", 0)
+        c.set_option("run_fraction_ppm", 0)
+        c.set_option("max_groups", groups)
+        c.set_option("kernel", kernel)
+        c.set_option("ring", 1 if groups == 1 else 4)  # ring 1: a row is gathered after the previous update
+        d = upload_ds(c, ds)
+        c.probe_arm(0)
+        c.sgd_epoch(d, 1e-3, 0.02, GB, mb.MODE_ATOMIC)
+        launch = c.last_launch()
+        assert launch["kernel"] == kernel
+        if kernel == 4:
+            c.close()  # the probe instruments the stream kernel only
+            continue
+        mean_all, mean_hot, updates = c.probe_read()
+        assert updates == n
+        if groups == 1:
+            assert mean_all == 0.0 and mean_hot == 0.0
+        else:
+            assert mean_hot > 1.0 and mean_hot > mean_all
+        c.close()
+
+
+def test_kernel_choice_follows_the_concurrency_bounds():
+    """Auto choice (kernel = 0): a launch the bounds keep narrow goes to the burst kernel, a wide one
+    to the stream kernel; rows outside 68..128 floats always to the stream kernel."""
+    nu, nv = 20000, 2000
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 1_000_000, test_frac=0.0))
+    c = mb.Context(nu, nv, 128)
+    c.init_normal(1, 1e-2)
+    d = c.dataset_from_blocks(tr)
+    c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)  # 80,000 runs: 0.35% = 280 in flight
+    assert c.last_launch()["kernel"] == 4
+    c.set_option("run_fraction_ppm", 0)
+    c.set_option("row_concurrency", 0)
+    c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)
+    assert c.last_launch()["kernel"] == 3
+    c.close()
+    c = mb.Context(nu, nv, 32)
+    c.init_normal(1, 1e-2)
+    d = c.dataset_from_blocks(tr)
+    c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)
+    assert c.last_launch()["kernel"] == 3
+    c.close()
