@@ -277,6 +277,9 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "batch")) {
     MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
     c->opt_batch = value;
+  } else if (!strcmp(name, "depth")) {
+    MFB_REQUIRE(value >= 0 && value <= 2, "depth must be 0 (choose), 1 or 2");
+    c->opt_depth = value;
   } else if (!strcmp(name, "ring")) {
     MFB_REQUIRE(value >= 0 && value <= 4, "ring must be 0..4");
     c->opt_ring = value;

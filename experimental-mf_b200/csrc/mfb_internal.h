@@ -116,6 +116,7 @@ struct Context {
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
   double rate_stream = 1.2e6, rate_burst = 5.0e6;  // updates/s per run in flight (measured; for the choice)
+  int opt_depth = 0;            // burst kernel: batches requested ahead (1, 2; 0 = choose)
   int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the
                                 // deepest ring the budget of the hottest row leaves room for)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,

@@ -76,25 +76,29 @@ __device__ __forceinline__ void burst_red1(float* p, float v) {
 
 }  // namespace
 
-// shared memory of one warp: two slots of (B item rows + B bias quads), two chunks of 32 record
-// ids/ratings, the prefetched factor row and bias quad of the next user
-template <int B>
+// shared memory of one warp: D+1 slots of (B item rows + B bias quads), three chunks of 32 record
+// ids/ratings, two prefetched factor rows + bias quads (the next two users)
+template <int B, int D>
 struct BurstSmem {
-  static constexpr int ROWS = 2 * B * 512;   // [slot][b][lane] float4
-  static constexpr int BIAS = 2 * B * 16;    // [slot][b] the 16 aligned bytes around bv[v]
-  static constexpr int CHUNK = 2 * 256;      // [buf][vid 32 x int | rating 32 x float]
-  static constexpr int PFT = 512 + 16;       // next user's row + the 16 aligned bytes around bu[u]
+  static constexpr int S = D + 1;
+  static constexpr int ROWS = S * B * 512;   // [slot][b][lane] float4
+  static constexpr int BIAS = S * B * 16;    // [slot][b] the 16 aligned bytes around bv[v]
+  static constexpr int CHUNK = 3 * 256;      // [buf][vid 32 x int | rating 32 x float]
+  static constexpr int PFT = 2 * (512 + 16); // [k]: a user's row + the 16 aligned bytes around bu[u]
   static constexpr int WARP_BYTES = ROWS + BIAS + CHUNK + PFT;
 };
 
 // EXACT: rows of exactly 32 float4 (k = 128): no lane predicates.
-template <int B, int MODE, bool EXACT>
+// D: batches requested ahead of the one being computed (1 or 2).
+template <int B, int D, int MODE, bool EXACT>
 __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const int nspans) {
-  using SM = BurstSmem<B>;
+  using SM = BurstSmem<B, D>;
+  constexpr int S = SM::S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool lane_ok = EXACT || lane < a.nvec;
+  const bool lane0 = lane == 0;
   const float eta = a.eta, lameta = a.lameta, lm1 = a.lm1, gb = a.gb;
   const int nvec = EXACT ? 32 : a.nvec;
   const float4* __restrict__ phi4 = reinterpret_cast<const float4*>(a.phi);
@@ -103,8 +107,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
   const uint32_t rows_me = wbase + lane * 16;           // + (slot*B + b)*512
   const uint32_t bias0 = wbase + SM::ROWS;              // + (slot*B + b)*16
   const uint32_t chunk0 = bias0 + SM::BIAS;             // + buf*256 (+128: ratings)
-  const uint32_t pft_me = chunk0 + SM::CHUNK + lane * 16;
-  const uint32_t pfb = chunk0 + SM::CHUNK + 512;
+  const uint32_t pft0 = chunk0 + SM::CHUNK;             // + k*528: row (lane*16), then the bias quad at +512
   {  // lanes beyond the row length never copy: their vectors must read as zeros
     float4* w = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * SM::WARP_BYTES);
     for (int q = lane; q < SM::WARP_BYTES / 16; q += 32) w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
   for (;;) {
     // ---- claim a span of 32 consecutive user-runs ---------------------------------------------
     int sp = 0;
-    if (lane == 0) sp = atomicAdd(a.counter, 1);
+    if (lane0) sp = atomicAdd(a.counter, 1);
     sp = __shfl_sync(FULL, sp, 0);
     if (sp >= nspans) break;
     int run0 = a.run_begin + sp * 32, span_n = 32;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       run0 = a.run_begin + a.big_spans * 32 + (sp - a.big_spans);
       span_n = 1;
     }
-    int s_uid = 0, s_end = 0;
+    int s_uid = 0, s_end = 0;  // per lane: user and record-end of run `lane` of the span
     if (lane < span_n) {
       s_uid = __ldg(a.run_uid + run0 + lane);
       s_end = __ldg(a.run_off + run0 + lane + 1);
@@ -132,8 +135,26 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     const int span_hi = __shfl_sync(FULL, s_end, span_n - 1);
     if (span_lo >= span_hi) continue;
 
-    // records [cbase, cbase+32) are in chunk buffer cbuf, the next 32 in the other one
-    int cbase = span_lo, cbuf = 0;
+    // next run with records after run i, whose predecessor ends at `prev_end` (runs without records
+    // share their predecessor's end); index span_n = none
+    auto next_run = [&](int i, int prev_end, int* end, int* user) {
+      int k = i + 1, e = 0;
+      for (;;) {
+        if (k >= span_n) break;
+        e = __shfl_sync(FULL, s_end, k & 31);
+        if (e != prev_end) break;
+        k++;
+      }
+      *end = e;
+      *user = k < span_n ? __shfl_sync(FULL, s_uid, k & 31) : -1;
+      return k;
+    };
+    // the factor row + bias of run-queue entry k go to prefetch slot `slot`
+    auto prefetch_user = [&](int slot, int user) {
+      if (lane_ok) cp_async16(pft0 + slot * 528 + lane * 16, theta4 + (int64_t)user * nvec + lane);
+      if (lane0) cp_async16(pft0 + slot * 528 + 512, a.bu + (user & ~3));
+    };
+    // records [32c, 32c+32) of the span live in chunk buffer c % 3
     auto chunk_fetch = [&](int buf, int q0) {
       const int q = q0 + lane;
       if (q < span_hi) {
@@ -141,115 +162,142 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
         cp_async4(chunk0 + buf * 256 + 128 + lane * 4, a.rating + q);
       }
     };
-    chunk_fetch(0, span_lo);
-    chunk_fetch(1, span_lo + 32);
-    // first non-empty run: its factor row comes through the same path as the prefetched ones
-    int ri = -1, cur_end = span_lo, uid = -1;
-    int nri = 0, n_end = 0, n_uid = -1, pf_iter = 0;
+
+    // ---- compute side: current run, the two runs after it (their rows are prefetched) -------------
+    int ri = -1, cur_end = span_lo, uid = -1, uid_before = -1;  // uid_before: user of the run before ri
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     float bu = 0.f;
-    // find the next non-empty run after ri (runs without records share their predecessor's end)
-    // and request its factor row and bias
-    auto prefetch_next_run = [&]() {
-      n_end = nri < span_n ? __shfl_sync(FULL, s_end, nri & 31) : 0;
-      while (nri < span_n && n_end == cur_end) {
-        nri++;
-        n_end = nri < span_n ? __shfl_sync(FULL, s_end, nri & 31) : 0;
-      }
-      if (nri < span_n) {
-        n_uid = __shfl_sync(FULL, s_uid, nri);
-        if (n_uid != uid) {  // (the same user again continues in registers)
-          if (lane_ok) cp_async16(pft_me, theta4 + (int64_t)n_uid * nvec + lane);
-          if (lane == 0) cp_async16(pfb, a.bu + (n_uid & ~3));
-          pf_iter = iter;
-        }
-      }
-    };
-    prefetch_next_run();
+    int up_i[2], up_end[2], up_uid[2], up_iter[2];
+    up_i[0] = next_run(-1, span_lo, &up_end[0], &up_uid[0]);
+    up_i[1] = next_run(up_i[0], up_end[0], &up_end[1], &up_uid[1]);
+    int nswitch = 0;  // run switches so far: the run entered at switch k has its row in slot k & 1
+    prefetch_user(0, up_uid[0]);
+    if (up_i[1] < span_n) prefetch_user(1, up_uid[1]);
+    up_iter[0] = up_iter[1] = iter - 8;  // both land before the loop starts (wait<0> below)
+    // ---- request side: cursor, run under the cursor, chunk under the cursor -----------------------
+    int jr = span_lo, rq_i = up_i[0], rq_end = up_end[0];
+    bool rq_start = true;  // the cursor stands at the first record of run rq_i
+    int rq_cbase = span_lo, rq_cbuf = 0;
+    chunk_fetch(0, span_lo);
+    chunk_fetch(1, span_lo + 32);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
 
-    // request the rows and bias quads of the batch [j0, j0+n) into slot p; ids/ratings -> registers
-    // Branch-free: a batch never crosses the 32-record chunk, so records idx .. idx+n-1 are in the
-    // buffer; slots b >= n are filled with the batch's last row again (never used).
-    auto request = [&](int p, int j0, int n, int (&vv)[B], float (&rr)[B]) {
-      const uint32_t cb = chunk0 + cbuf * 256 + ((j0 - cbase) & 31) * 4;
-      const bool lane0 = lane == 0;
+    // request the next batch (rows + bias quads) into ring slot `slot`; returns its descriptor.
+    // Branch-free inside: a batch never crosses a run or a 32-record chunk; ring entries b >= n are
+    // filled with the batch's last row again (never used).
+    auto request = [&](int slot, int* qj, int* qnew, int* qbuf) {
+      if (jr >= span_hi) return 0;
+      if (jr == rq_cbase + 32) {  // entering the next chunk: fetch the one after it over the oldest
+        rq_cbase += 32;
+        rq_cbuf = rq_cbuf == 2 ? 0 : rq_cbuf + 1;
+        chunk_fetch(rq_cbuf == 2 ? 0 : rq_cbuf + 1, rq_cbase + 32);
+      }
+      const int n = min(B, min(rq_end, rq_cbase + 32) - jr);
+      const uint32_t cb = chunk0 + rq_cbuf * 256 + (jr - rq_cbase) * 4;
 #pragma unroll
       for (int b = 0; b < B; b++) {
-        const uint32_t at = cb + min(b, n - 1) * 4;
-        vv[b] = lds1i(at);
-        rr[b] = lds1(at + 128);
-        if (lane_ok) cp_async16(rows_me + (p * B + b) * 512, phi4 + (int64_t)vv[b] * nvec + lane);
-        if (lane0) cp_async16(bias0 + (p * B + b) * 16, a.bv + (vv[b] & ~3));
+        const int vv = lds1i(cb + min(b, n - 1) * 4);
+        if (lane_ok) cp_async16(rows_me + (slot * B + b) * 512, phi4 + (int64_t)vv * nvec + lane);
+        if (lane0) cp_async16(bias0 + (slot * B + b) * 16, a.bv + (vv & ~3));
       }
+      *qj = jr;
+      *qnew = rq_start;
+      *qbuf = rq_cbuf;
+      jr += n;
+      rq_start = false;
+      if (jr == rq_end && jr < span_hi) {
+        int dummy;
+        rq_i = next_run(rq_i, rq_end, &rq_end, &dummy);
+        rq_start = true;
+      }
+      return n;
     };
 
-    int j = span_lo, p = 0;
-    bool cur_new_run = true;  // the current batch opens run nri
-    int nb = min(B, min(n_end, cbase + 32) - j);
-    int v[B];
-    float r[B];
-    request(0, j, nb, v, r);
-    cp_async_commit();
+    // ---- prime: D batches requested, one group each ------------------------------------------------
+    int qj[D], qnb[D], qnew[D], qbuf[D];
+    int sr = 0, sc = 0;  // ring slots of the next request / the next batch to compute
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      qj[d] = qnew[d] = qbuf[d] = 0;
+      qnb[d] = request(sr, &qj[d], &qnew[d], &qbuf[d]);
+      sr = sr == S - 1 ? 0 : sr + 1;
+      cp_async_commit();
+    }
 
     for (;;) {
-      // ---- run switch: the batch about to be computed opens run nri ----------------------------------
-      if (cur_new_run) {
+      const int j = qj[0], nb = qnb[0], cbuf = qbuf[0];
+      if (nb == 0) break;
+      // ---- run switch: the batch about to be computed opens run up_i[0] ---------------------------
+      if (qnew[0]) {
         if (ri >= 0) {
           if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
-          if (lane == 0) __stcg(a.bu + uid, bu);
+          if (lane0) __stcg(a.bu + uid, bu);
         }
-        if (n_uid != uid) {
-          if (iter - pf_iter < 2) {  // requested less than two batches ago (a run of one batch)
+        const int nuid = up_uid[0];
+        if (nuid == uid) {
+          // the same user again: theta/bu continue in registers
+        } else if (nuid == uid_before) {
+          // its row was prefetched before the run in between (same user) wrote it back: reload
+          t = lane_ok ? __ldcg(theta4 + (int64_t)nuid * nvec + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bu = __ldcg(a.bu + nuid);
+        } else {
+          if (iter - up_iter[0] < D + 1) {  // requested too recently for wait<D> to cover it (short runs)
             cp_async_wait<0>();
             __syncwarp();
           }
-          t = lds4(pft_me);
-          bu = lds1(pfb + (n_uid & 3) * 4);
+          const uint32_t at = pft0 + (nswitch & 1) * 528;
+          t = lds4(at + lane * 16);
+          bu = lds1(at + 512 + (nuid & 3) * 4);
         }
-        uid = n_uid;
-        ri = nri;
-        cur_end = n_end;
-        nri = ri + 1;
-        prefetch_next_run();
+        uid_before = uid;
+        uid = nuid;
+        ri = up_i[0];
+        cur_end = up_end[0];
+        up_i[0] = up_i[1];
+        up_end[0] = up_end[1];
+        up_uid[0] = up_uid[1];
+        up_iter[0] = up_iter[1];
+        up_i[1] = next_run(up_i[0], up_end[0], &up_end[1], &up_uid[1]);
+        if (up_i[1] < span_n) prefetch_user(nswitch & 1, up_uid[1]);  // the slot just read
+        up_iter[1] = iter;
+        nswitch++;
       }
-      // ---- request the next batch [j1, j1+nb1) while this one is computed -------------------------
-      const int j1 = j + nb;
-      const bool more = j1 < span_hi;
-      const bool next_new_run = more && j1 == cur_end;
-      int nb1 = 0;
-      int vn[B];
-      float rn[B];
-      if (more) {
-        if (j1 == cbase + 32) {  // the other buffer holds the next 32 records; refill this one
-          chunk_fetch(cbuf, cbase + 64);
-          cbuf ^= 1;
-          cbase += 32;
-        }
-        nb1 = min(B, min(next_new_run ? n_end : cur_end, cbase + 32) - j1);
-        request(p ^ 1, j1, nb1, vn, rn);
+      // ---- request the batch D ahead while this one is computed -----------------------------------
+#pragma unroll
+      for (int d = 0; d + 1 < D; d++) {
+        qj[d] = qj[d + 1];
+        qnb[d] = qnb[d + 1];
+        qnew[d] = qnew[d + 1];
+        qbuf[d] = qbuf[d + 1];
       }
+      qnb[D - 1] = request(sr, &qj[D - 1], &qnew[D - 1], &qbuf[D - 1]);
+      sr = sr == S - 1 ? 0 : sr + 1;
       cp_async_commit();
       iter++;
-      cp_async_wait<1>();  // everything but the requests just made has landed
+      cp_async_wait<D>();  // everything but the D newest requests has landed
       __syncwarp();
 
       // ---- this batch: all inner products at once, residuals by recurrence, row updates ---------------
       auto compute = [&](auto full_tag) {
         constexpr bool FULLB = decltype(full_tag)::value;  // all B records present: no per-record tests
+        const uint32_t cb = chunk0 + cbuf * 256 + ((j - span_lo) & 31) * 4;
         float4 f[B];
-        float bvv[B];
+        float bvv[B], r[B];
+        int v[B];
 #pragma unroll
         for (int b = 0; b < B; b++) {
-          f[b] = lds4(rows_me + (p * B + b) * 512);
-          bvv[b] = lds1(bias0 + (p * B + b) * 16 + (v[b] & 3) * 4);
+          const uint32_t at = cb + (FULLB ? b : min(b, nb - 1)) * 4;
+          v[b] = lds1i(at);
+          r[b] = lds1(at + 128);
+          f[b] = lds4(rows_me + (sc * B + b) * 512);
+          bvv[b] = lds1(bias0 + (sc * B + b) * 16 + (v[b] & 3) * 4);
         }
-        float D[B], G[B][B];
+        float D_[B], G[B][B];
 #pragma unroll
         for (int b = 0; b < B; b++) {
-          D[b] = dot4(t, f[b]);
+          D_[b] = dot4(t, f[b]);
 #pragma unroll
           for (int c = b + 1; c < B; c++) G[b][c] = dot4(f[b], f[c]);
         }
@@ -257,7 +305,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
           for (int b = 0; b < B; b++) {
-            D[b] += __shfl_xor_sync(FULL, D[b], o);
+            D_[b] += __shfl_xor_sync(FULL, D_[b], o);
 #pragma unroll
             for (int c = b + 1; c < B; c++) G[b][c] += __shfl_xor_sync(FULL, G[b][c], o);
           }
@@ -269,7 +317,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
 #pragma unroll
         for (int b = 0; b < B; b++) {
           if (FULLB || b < nb) {
-            float d = tpow * D[b];
+            float d = tpow * D_[b];
 #pragma unroll
             for (int c = 0; c < b; c++) d = fmaf(coef[c], G[c][b], d);
             const float e = eta * (((r[b] - bvv[b] - gb) - d) - bu);
@@ -297,21 +345,11 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       };
       if (nb == B) compute(std::true_type{});
       else compute(std::false_type{});
-
-      if (!more) break;
-      j = j1;
-      nb = nb1;
-      p ^= 1;
-      cur_new_run = next_new_run;
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        r[b] = rn[b];
-        v[b] = vn[b];
-      }
+      sc = sc == S - 1 ? 0 : sc + 1;
     }
     // last run of the span
     if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
-    if (lane == 0) __stcg(a.bu + uid, bu);
+    if (lane0) __stcg(a.bu + uid, bu);
     cp_async_wait<0>();  // nothing of this span may land in the buffers of the next one
     __syncwarp();
   }
@@ -320,23 +358,25 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
 // ------------------------------------------------------------------------------------------
 namespace {
 
-template <int B>
+template <int B, int D>
 int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   const bool exact = a.nvec == 32;
   const void* k = mode == MFB_MODE_ATOMIC
-                      ? (exact ? (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC, true>
-                               : (const void*)sgd_burst_kernel<B, MFB_MODE_ATOMIC, false>)
-                      : (exact ? (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, true>
-                               : (const void*)sgd_burst_kernel<B, MFB_MODE_HOGWILD, false>);
+                      ? (exact ? (const void*)sgd_burst_kernel<B, D, MFB_MODE_ATOMIC, true>
+                               : (const void*)sgd_burst_kernel<B, D, MFB_MODE_ATOMIC, false>)
+                      : (exact ? (const void*)sgd_burst_kernel<B, D, MFB_MODE_HOGWILD, true>
+                               : (const void*)sgd_burst_kernel<B, D, MFB_MODE_HOGWILD, false>);
   const int nruns = a.nruns - a.run_begin;
   int per_sm = 0;
-  constexpr int WARP_BYTES = BurstSmem<B>::WARP_BYTES;
+  constexpr int WARP_BYTES = BurstSmem<B, D>::WARP_BYTES;
+  if (4 * WARP_BYTES > 48 * 1024)
+    MFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * WARP_BYTES));
   MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * WARP_BYTES));
   per_sm = std::max(per_sm, 1);
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
   int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max((nruns + 31) / 32, 1));
-  // a run holds the current batch and the requested one: 2B item rows between gather and reduction
-  warps = bounded_groups(c, warps, d->max_item_share, d->nruns, 2.0 * B, a.eta);
+  // a run holds the batch being computed and the D requested ones between gather and reduction
+  warps = bounded_groups(c, warps, d->max_item_share, d->nruns, (double)(D + 1) * B, a.eta);
   SgdArgs aa = a;
   aa.big_spans = (int)std::max<int64_t>(0, (nruns - 2 * warps) / 32);  // ~2 single runs per warp at the end
   const int nspans = aa.big_spans + (nruns - aa.big_spans * 32);
@@ -352,7 +392,7 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   }
   c->last_grid = grid;
   c->last_threads = threads;
-  c->last_ring = B;
+  c->last_ring = B * 10 + D;
   void* args[] = {(void*)&aa, (void*)&nspans};
   MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
   MFB_CUDA(cudaGetLastError());
@@ -365,8 +405,17 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
 int launch_sgd_burst(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled) {
   *handled = a.nvec > 16 && a.nvec <= 32;  // rows of 68..128 floats: one float4 per lane
   if (!*handled) return MFB_OK;
-  if (c->opt_batch == 8) return launch_burst_t<8>(c, d, a, mode);
-  return launch_burst_t<4>(c, d, a, mode);
+  // depth: batches requested ahead.  2 hides the L2 latency of a loaded machine; it also holds one
+  // more batch of rows in flight per run, so when the budget of the hottest row (not the run bound)
+  // limits the launch, depth 1 keeps more runs in flight.
+  int depth = c->opt_depth;
+  if (depth == 0) {
+    const int64_t cap = (int64_t)c->sm_count * 64;
+    const int64_t run_only = bounded_groups(c, cap, 0.0, d->nruns, 1.0, a.eta);
+    depth = bounded_groups(c, cap, d->max_item_share, d->nruns, 3.0 * c->opt_batch, a.eta) >= run_only ? 2 : 1;
+  }
+  if (c->opt_batch == 8) return depth == 2 ? launch_burst_t<8, 2>(c, d, a, mode) : launch_burst_t<8, 1>(c, d, a, mode);
+  return depth == 2 ? launch_burst_t<4, 2>(c, d, a, mode) : launch_burst_t<4, 1>(c, d, a, mode);
 }
 
 }  // namespace mfb

@@ -11,10 +11,10 @@ tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz))
 c = mb.Context(nu, nv, k)
 dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
 for W in (210, 420, 840, 1680, 3360):
-    for kern, ring in ((2, 0), (3, 2), (4, 4), (4, 8)):
+    for kern, ring in ((3, 2), (4, 14), (4, 24)):
         c.set_option("kernel", kern); c.set_option("max_groups", W)
         if kern == 3: c.set_option("ring", ring)
-        if kern == 4: c.set_option("batch", ring)
+        if kern == 4: c.set_option("batch", ring % 10); c.set_option("depth", ring // 10)
         c.init_normal(1, 1e-2)
         ms = []
         for ep in (1, 2):
