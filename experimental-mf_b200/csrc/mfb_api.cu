@@ -551,10 +551,10 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC, "streamed epochs are Hogwild/atomic only");
   MFB_CUDA(cudaSetDevice(c->device));
   if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  if (chunk_ratings <= 0) chunk_ratings = 8 << 20;
-  // chunks grow geometrically (x1, x2, x4, x8 the given size, then constant): the first kernel starts
-  // after a small copy, and there are few launches (each has a ramp and a tail)
-  const int64_t max_chunk = chunk_ratings * 8;
+  if (chunk_ratings <= 0) chunk_ratings = 2 << 20;
+  // chunks grow geometrically (x1, x4, x16, x32 the given size, then constant): the first kernel
+  // starts after a small copy, and there are few launches (each has a ramp and a tail)
+  const int64_t max_chunk = chunk_ratings * 32;
   begin_timing(c);
   // the copy stream must not overwrite tiles that work queued earlier on the main stream still reads
   cudaEvent_t start_ev;
@@ -589,7 +589,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   while (r0 < d->nruns) {
     int64_t r1 = r0;
     const int64_t o0 = s->h_run_off[r0];
-    const int64_t want = std::min(max_chunk, chunk_ratings << std::min<size_t>(chunk, 3));
+    const int64_t want = std::min(max_chunk, chunk_ratings << (2 * std::min<size_t>(chunk, 3)));
     {  // last run whose end is within `want` records (run_off is sorted)
       const int32_t* ro = s->h_run_off.data();
       r1 = std::upper_bound(ro + r0 + 1, ro + d->nruns + 1, (int32_t)std::min<int64_t>(o0 + want, INT32_MAX)) - ro - 1;

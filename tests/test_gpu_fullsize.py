@@ -89,7 +89,7 @@ def test_streamed_epoch_equals_resident_epoch_at_full_size(data):
                 c.sgd_epoch(dtr, eta, 5e-3, GB, mb.MODE_ATOMIC)
         got.append(c.rmse(dte, GB))
         if streamed:
-            assert c.h2d_bytes() == 2 * (3 * tr.nratings + 8 * tr.nruns + 4 * 4)  # 3-byte records, 4 chunks (8+16+32+64 M)
+            assert c.h2d_bytes() == 2 * (3 * tr.nratings + 8 * tr.nruns + 4 * 4)  # 3-byte records, 4 chunks (2+8+32+64 M)
         c.close()
     tr.unpin()
     assert abs(got[0] - got[1]) <= 5e-4, got
