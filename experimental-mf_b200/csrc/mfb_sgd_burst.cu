@@ -85,7 +85,8 @@ struct BurstSmem {
   static constexpr int BIAS = S * B * 16;    // [slot][b] the 16 aligned bytes around bv[v]
   static constexpr int CHUNK = 3 * 256;      // [buf][vid 32 x int | rating 32 x float]
   static constexpr int PFT = 2 * (512 + 16); // [k]: a user's row + the 16 aligned bytes around bu[u]
-  static constexpr int WARP_BYTES = ROWS + BIAS + CHUNK + PFT;
+  static constexpr int VER = S * B * 4;      // staleness probe: item version at request time
+  static constexpr int WARP_BYTES = ROWS + BIAS + CHUNK + PFT + VER;
 };
 
 // EXACT: rows of exactly 32 float4 (k = 128): no lane predicates.
@@ -108,6 +109,9 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
   const uint32_t bias0 = wbase + SM::ROWS;              // + (slot*B + b)*16
   const uint32_t chunk0 = bias0 + SM::BIAS;             // + buf*256 (+128: ratings)
   const uint32_t pft0 = chunk0 + SM::CHUNK;             // + k*528: row (lane*16), then the bias quad at +512
+  int* const ver = reinterpret_cast<int*>(smem_raw + (threadIdx.x >> 5) * SM::WARP_BYTES + SM::ROWS + SM::BIAS +
+                                          SM::CHUNK + SM::PFT);  // [slot*B + b]
+  unsigned long long pr_sum = 0, pr_n = 0, pr_hsum = 0, pr_hn = 0;
   {  // lanes beyond the row length never copy: their vectors must read as zeros
     float4* w = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * SM::WARP_BYTES);
     for (int q = lane; q < SM::WARP_BYTES / 16; q += 32) w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
         const int vv = lds1i(cb + min(b, n - 1) * 4);
         if (lane_ok) cp_async16(rows_me + (slot * B + b) * 512, phi4 + (int64_t)vv * nvec + lane);
         if (lane0) cp_async16(bias0 + (slot * B + b) * 16, a.bv + (vv & ~3));
+        if (a.version && lane0) ver[slot * B + b] = __ldcg(a.version + vv);
       }
       *qj = jr;
       *qnew = rq_start;
@@ -342,6 +347,19 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
           }
         }
         if (lane < (FULLB ? B : nb)) burst_red1(a.bv + my_v, my_bias);
+        if (a.version && lane0) {  // staleness probe: updates of the item performed since its row was requested
+#pragma unroll
+          for (int b = 0; b < B; b++)
+            if (FULLB || b < nb) {
+              const int seen = atomicAdd(a.version + v[b], 1) - ver[sc * B + b];
+              pr_sum += (unsigned)seen;
+              pr_n++;
+              if (v[b] == a.probe_item) {
+                pr_hsum += (unsigned)seen;
+                pr_hn++;
+              }
+            }
+        }
       };
       if (nb == B) compute(std::true_type{});
       else compute(std::false_type{});
@@ -352,6 +370,12 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     if (lane0) __stcg(a.bu + uid, bu);
     cp_async_wait<0>();  // nothing of this span may land in the buffers of the next one
     __syncwarp();
+  }
+  if (a.version && lane0) {
+    atomicAdd(a.probe_out + 0, pr_sum);
+    atomicAdd(a.probe_out + 1, pr_n);
+    atomicAdd(a.probe_out + 2, pr_hsum);
+    atomicAdd(a.probe_out + 3, pr_hn);
   }
 }
 
