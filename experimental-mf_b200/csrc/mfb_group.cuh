@@ -16,7 +16,7 @@ template <int LPR>
 __device__ __forceinline__ unsigned group_mask() {
   if (LPR == 32) return 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
+  return ((1u << (LPR & 31)) - 1u) << (lane & ~(LPR - 1));
 }
 
 // butterfly sum over the group; every lane ends with the total

@@ -42,9 +42,6 @@ __device__ __forceinline__ void red_add4(float4* p, const float4& v) {
 __device__ __forceinline__ void red_add4p(float4* p, const float4& v, bool on) {
   if (on) red_add4(p, v);
 }
-__device__ __forceinline__ void red_add1(float* p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
 // the same with the old value returned: its arrival tells the issuer that the L2 has performed it
 __device__ __forceinline__ float atom_add1(float* p, float v) {
   float old;
@@ -55,7 +52,7 @@ __device__ __forceinline__ float atom_add1(float* p, float v) {
 template <int LPR>
 __device__ __forceinline__ unsigned sub_mask(int lane) {
   if (LPR == 32) return 0xffffffffu;
-  return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
+  return ((1u << (LPR & 31)) - 1u) << (lane & ~(LPR - 1));
 }
 
 // ---- cp.async helpers (LDGSTS): global -> shared without passing through registers ------------

@@ -65,15 +65,36 @@ __device__ __forceinline__ Row<VPL> noise_row(const SgldArgs& a, int kind, int r
     if (c + 2 >= a.dim) z.v[i].z = 0.f;
     if (c + 3 >= a.dim) z.v[i].w = 0.f;
   }
-  // the bias value: lane 0 evaluates chunk MFB_BIAS_CHUNK of the same (kind,row,t) stream
+  // the bias value: chunk MFB_BIAS_CHUNK of the same (kind,row,t) stream, evaluated by lane 0 and
+  // handed to every lane of the group (all of them carry the bias)
+  if (bias_noise) {
+    float b = 0.f;
+    if (gl == 0) {
+      const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)row, MFB_BIAS_CHUNK, (uint32_t)kind + 2u * a.round),
+                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+      b = (FAST ? box_muller4_fast(x) : box_muller4(x)).x;
+    }
+    *bias_noise = __shfl_sync(group_mask<LPR>(), b, 0, LPR);
+  }
+  return z;
+}
+
+// Both rows of one record: user noise (kind 0, row uid) and item noise (kind 1, row v) at logical time
+// t.  The two bias values are evaluated in ONE pass - lane 0 the user's, lane 1 the item's - instead
+// of two passes that keep 31 lanes idle each.
+template <int LPR, int VPL, bool FAST>
+__device__ __forceinline__ void noise_pair(const SgldArgs& a, int uid, int v, int t, int gl, unsigned m,
+                                           Row<VPL>& xu, Row<VPL>& xv, float* xbu, float* xbv) {
+  xu = noise_row<LPR, VPL, FAST>(a, 0, uid, t, gl, nullptr);
+  xv = noise_row<LPR, VPL, FAST>(a, 1, v, t, gl, nullptr);
   float b = 0.f;
-  if (gl == 0) {
-    const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)row, MFB_BIAS_CHUNK, (uint32_t)kind + 2u * a.round),
+  if (gl < 2) {
+    const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(gl ? v : uid), MFB_BIAS_CHUNK, (uint32_t)gl + 2u * a.round),
                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
     b = (FAST ? box_muller4_fast(x) : box_muller4(x)).x;
   }
-  *bias_noise = b;
-  return z;
+  *xbu = __shfl_sync(m, b, 0, LPR);
+  *xbv = __shfl_sync(m, b, 1, LPR);
 }
 
 // table source of the ordered parity mode: values [ind, ind+dim] of the reference's noise_ table
@@ -156,15 +177,36 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
     const float au = -a.eta * ur * a.bound;                                       // dpmf.h:78
     const double cbu = 1.0 - (double)(a.eta * a.lambda_ub * ur * a.bound);        // dpmf.h:84
     int uc = __ldg(a.run_uc + run);
+    // records are read LPR at a time (one per lane); in the parallel schedule the item row, bias and
+    // weight of record j+1 are requested before the noise of record j is evaluated (~350
+    // instructions of pure arithmetic), so their latency is hidden behind it
+    int myvid = 0, myvc = 0, v_n = 0;
+    float myr = 0.f, bv_n = 0.f, vr_n = 0.f;
+    Row<VPL> f_n;
+    auto fetch = [&](int b) {
+      v_n = __shfl_sync(m, myvid, b & (LPR - 1), LPR);
+      f_n = load_row<LPR, VPL>(a.phi, v_n, a.nvec, gl);
+      bv_n = (gl == 0) ? __ldcg(a.bv + v_n) : 0.f;
+      vr_n = __ldg(a.vr + v_n);
+    };
     for (int j = lo; j < hi; j++) {
-      const int v = __ldcs(a.vid + j);
-      const float r = __ldcs(a.rating + j);
-      const int vc = __ldcs(a.vc + j);
-      Row<VPL> f = load_row<LPR, VPL>(a.phi, v, a.nvec, gl);
+      const int b = (j - lo) & (LPR - 1);
+      if (b == 0) {
+        const int q = j + gl;
+        myvid = q < hi ? __ldcs(a.vid + q) : 0;
+        myr = q < hi ? __ldcs(a.rating + q) : 0.f;
+        myvc = q < hi ? __ldcs(a.vc + q) : 0;
+      }
+      if (ORDERED || b == 0) fetch(b);  // the ordered schedule reads every row after the previous update
+      const int v = v_n;
+      const float r = __shfl_sync(m, myr, b, LPR);
+      const int vc = __shfl_sync(m, myvc, b, LPR);
+      Row<VPL> f = f_n;
       const Row<VPL> f_in = f;
-      float bvv = (gl == 0) ? __ldcg(a.bv + v) : 0.f;
+      float bvv = bv_n;
       const float bv_in = bvv;
-      const float vr = __ldg(a.vr + v);
+      const float vr = vr_n;
+      if (!ORDERED && b + 1 < LPR && j + 1 < hi) fetch(b + 1);  // (items of one run are distinct)
       const float av = -a.eta * vr * a.bound;                                     // dpmf.h:81
       const double cbv = 1.0 - (double)(a.eta * a.lambda_vb * vr * a.bound);      // dpmf.h:85
       const float su = sqrtf(a.temp * a.eta * uc), sv = sqrtf(a.temp * a.eta * vc);  // dpmf.h:67-70
@@ -176,8 +218,7 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
         xv = xu;
         xbv = xbu;
       } else {
-        xu = noise_row<LPR, VPL, !ORDERED>(a, 0, uid, j, gl, &xbu);
-        xv = noise_row<LPR, VPL, !ORDERED>(a, 1, v, j, gl, &xbv);
+        noise_pair<LPR, VPL, !ORDERED>(a, uid, v, j, gl, m, xu, xv, &xbu, &xbv);
       }
       if (ORDERED) {
         // the oracle's operation order, every product and sum rounded on its own

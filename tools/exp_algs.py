@@ -15,7 +15,9 @@ for k, eps in ((128, 0.0), (64, 1.0)):   # config 3: pure SGLD k=128; config 4: 
     ntrain = c.dp_weights(d)
     bound = mb.lib().mfb_dp_bound(eps, 0, nv)
     lam = np.full(k, 1e2, np.float32); c.upload(mb.LAMBDA_U, lam); c.upload(mb.LAMBDA_V, lam)
-    eta0, temp, gam = np.float32(2e-2 / ntrain / bound), np.float32(0.1), 1.0
+    # effective step scal = eta*ntrain*bound = 0.02 as in plain SGD; noise variance per epoch and
+    # coordinate temp*eta*ntrain = 0.002 (the reference's sweep: temp 0.1, eta of order 1/ntrain, run.py:22,34)
+    eta0, temp, gam = np.float32(2e-2 / ntrain / bound), np.float32(0.1 * bound), 1.0
     ms, fl, traj = [], [], []
     for ep in range(1, 5):
         eta = mb.lib().mfb_seteta_cutoff(eta0, ep, gam, 1e-13)
