@@ -164,7 +164,10 @@ int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks**
   return MFB_OK;
 }
 
-void mfb_blocks_free(mfb_blocks* b) { delete b; }
+void mfb_blocks_free(mfb_blocks* b) {
+  if (b && b->d.pinned) mfb_blocks_unpin(b);  // also releases the page-locked compact copy
+  delete b;
+}
 int64_t mfb_blocks_num_blocks(const mfb_blocks* b) { return b ? (int64_t)b->d.h_block_off.size() - 1 : -1; }
 int64_t mfb_blocks_num_runs(const mfb_blocks* b) { return b ? (int64_t)b->d.h_run_uid.size() : -1; }
 int64_t mfb_blocks_num_ratings(const mfb_blocks* b) { return b ? (int64_t)b->d.h_vid.size() : -1; }

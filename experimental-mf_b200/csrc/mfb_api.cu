@@ -51,8 +51,18 @@ static int alloc_array(Context* c, int which) {
   return MFB_OK;
 }
 
+static int64_t bounded_groups_alone(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
+                                    double inflight, float eta);
+
 int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
                        double inflight, float eta) {
+  const int64_t g = bounded_groups_alone(c, groups, max_item_share, total_runs, inflight, eta);
+  // width_div > 1: this launch shares the machine and the bounds with concurrent ones
+  return std::max<int64_t>(1, g / std::max(c->width_div, 1));
+}
+
+static int64_t bounded_groups_alone(const Context* c, int64_t groups, double max_item_share, int64_t total_runs,
+                                    double inflight, float eta) {
   if (c->opt_max_groups > 0) return std::min<int64_t>(groups, c->opt_max_groups);
   // both budgets are on (step size) x (stale updates applied at once): they widen as eta decays
   const double widen = (c->opt_eta_scaling && eta > 0.f) ? 0.02 / (double)eta : 1.0;
@@ -227,10 +237,11 @@ void mfb_destroy(mfb_ctx* h) {
   cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_s2) cudaEventDestroy(c->ev_s2);
   for (int b = 0; b < 2; b++) {
     cudaFree(c->d_stage_vid[b]);
     cudaFree(c->d_stage_code[b]);
-    if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
   }
   cudaFree(c->d_dict);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
@@ -277,6 +288,14 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "batch")) {
     MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
     c->opt_batch = value;
+  } else if (!strcmp(name, "two_streams")) {
+    c->opt_two_streams = value != 0;
+  } else if (!strcmp(name, "epoch_launches")) {
+    MFB_REQUIRE(value >= 1 && value <= 4096, "epoch_launches out of range");
+    c->opt_epoch_launches = value;
+  } else if (!strcmp(name, "tail_runs")) {
+    MFB_REQUIRE(value >= 0 && value <= 1024, "tail_runs out of range");
+    c->opt_tail_runs = value;
   } else if (!strcmp(name, "depth")) {
     MFB_REQUIRE(value >= 0 && value <= 2, "depth must be 0 (choose), 1 or 2");
     c->opt_depth = value;
@@ -529,7 +548,12 @@ int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mod
               "bad mode %d", mode);
   MFB_CUDA(cudaSetDevice(c->device));
   begin_timing(c);
-  int rc = d->nruns ? launch_sgd(c, d, eta, lambda, gb, mode, 0, d->nruns) : MFB_OK;
+  int rc = MFB_OK;
+  const int64_t parts = std::max(1, c->opt_epoch_launches);  // diagnostic: the epoch as several launches
+  for (int64_t k = 0; k < parts && rc == MFB_OK && d->nruns; k++) {
+    const int64_t r0 = d->nruns * k / parts, r1 = d->nruns * (k + 1) / parts;
+    if (r1 > r0) rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
+  }
   end_timing(c);
   return rc;
 }
@@ -551,12 +575,21 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC, "streamed epochs are Hogwild/atomic only");
   MFB_CUDA(cudaSetDevice(c->device));
   if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  if (chunk_ratings <= 0) chunk_ratings = 2 << 20;
-  // chunks grow geometrically (x1, x4, x16, x32 the given size, then constant): the first kernel
-  // starts after a small copy, and there are few launches (each has a ramp and a tail)
-  const int64_t max_chunk = chunk_ratings * 32;
+  if (chunk_ratings <= 0) chunk_ratings = 3 << 20;
+  // Chunks grow geometrically by 7/4 up to 6x the given size: the first kernel starts after a small
+  // copy and every later copy is shorter than the kernels it hides behind (measured while kernels
+  // run: H2D ~35 GB/s = 11.7 G packed records/s against 6.5 G updates/s).
+  // Each launch ends with a tail - the longest user-run still in flight, ~0.9 ms at this shape
+  // (tools/exp_launches.py) - so consecutive chunks go to TWO compute streams at half the width
+  // each: the tail of one chunk overlaps the body of the next, and the sum of the runs in flight
+  // stays within the concurrency bounds.
+  const int64_t max_chunk = chunk_ratings * 6;
   begin_timing(c);
-  // the copy stream must not overwrite tiles that work queued earlier on the main stream still reads
+  if (!c->stream2) {
+    MFB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    MFB_CUDA(cudaEventCreateWithFlags(&c->ev_s2, cudaEventDisableTiming));
+  }
+  // neither the copy stream nor the second compute stream may run ahead of work queued earlier
   cudaEvent_t start_ev;
   if (c->chunk_events.empty()) {
     cudaEvent_t e;
@@ -566,6 +599,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   start_ev = c->chunk_events[0];
   MFB_CUDA(cudaEventRecord(start_ev, c->stream));
   MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, start_ev, 0));
+  MFB_CUDA(cudaStreamWaitEvent(c->stream2, start_ev, 0));
   const bool packed = s->packed && c->opt_packed_h2d;
   if (packed) {
     if (c->stage_capacity < max_chunk + 65536) {
@@ -577,19 +611,22 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
         cudaFree(c->d_stage_code[b]);
         MFB_CUDA(cudaMalloc(&c->d_stage_vid[b], c->stage_capacity * sizeof(uint16_t)));
         MFB_CUDA(cudaMalloc(&c->d_stage_code[b], c->stage_capacity));
-        if (!c->stage_free[b]) MFB_CUDA(cudaEventCreateWithFlags(&c->stage_free[b], cudaEventDisableTiming));
       }
       if (!c->d_dict) MFB_CUDA(cudaMalloc(&c->d_dict, 256 * sizeof(float)));
     }
     MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
-    for (int b = 0; b < 2; b++) MFB_CUDA(cudaEventRecord(c->stage_free[b], c->stream));
   }
+  cudaStream_t const main_stream = c->stream;
+  const bool two = c->opt_two_streams != 0;
+  int rc = MFB_OK;
   int64_t r0 = 0;
   size_t chunk = 0;
-  while (r0 < d->nruns) {
+  while (r0 < d->nruns && rc == MFB_OK) {
     int64_t r1 = r0;
     const int64_t o0 = s->h_run_off[r0];
-    const int64_t want = std::min(max_chunk, chunk_ratings << (2 * std::min<size_t>(chunk, 3)));
+    int64_t want = chunk_ratings;
+    for (size_t g = 0; g < chunk && want < max_chunk; g++) want = want * 7 / 4;
+    want = std::min(want, max_chunk);
     {  // last run whose end is within `want` records (run_off is sorted)
       const int32_t* ro = s->h_run_off.data();
       r1 = std::upper_bound(ro + r0 + 1, ro + d->nruns + 1, (int32_t)std::min<int64_t>(o0 + want, INT32_MAX)) - ro - 1;
@@ -602,18 +639,24 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
                              cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(d->d_run_off + r0, s->h_run_off.data() + r0, (r1 - r0 + 1) * sizeof(int32_t),
                              cudaMemcpyHostToDevice, c->copy_stream));
-    if (staged) {  // 3 bytes per record into the staging buffer, expanded on the device
-      MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->stage_free[sb], 0));
-      MFB_CUDA(cudaMemcpyAsync(c->d_stage_vid[sb], s->p_vid.data() + o0, (o1 - o0) * sizeof(uint16_t),
+    if (staged) {  // 3 bytes per record into a staging buffer, expanded by a kernel on the copy stream
+      MFB_CUDA(cudaMemcpyAsync(c->d_stage_vid[sb], s->p_vid + o0, (o1 - o0) * sizeof(uint16_t),
                                cudaMemcpyHostToDevice, c->copy_stream));
-      MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code.data() + o0, (o1 - o0), cudaMemcpyHostToDevice,
+      MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code + o0, (o1 - o0), cudaMemcpyHostToDevice,
                                c->copy_stream));
+      c->stream = c->copy_stream;  // (stream order frees the staging buffer for the copy after next)
+      rc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid + o0, d->d_rating + o0, o1 - o0);
+      c->stream = main_stream;
+      if (rc) break;
+      c->h2d_bytes += (o1 - o0) * 3;
     } else {
       MFB_CUDA(cudaMemcpyAsync(d->d_vid + o0, s->h_vid.data() + o0, (o1 - o0) * sizeof(int32_t),
                                cudaMemcpyHostToDevice, c->copy_stream));
       MFB_CUDA(cudaMemcpyAsync(d->d_rating + o0, s->h_rating.data() + o0, (o1 - o0) * sizeof(float),
                                cudaMemcpyHostToDevice, c->copy_stream));
+      c->h2d_bytes += (o1 - o0) * 8;
     }
+    c->h2d_bytes += (r1 - r0) * 8 + 4;
     ++chunk;
     if (c->chunk_events.size() <= chunk) {
       cudaEvent_t e;
@@ -621,20 +664,22 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
       c->chunk_events.push_back(e);
     }
     MFB_CUDA(cudaEventRecord(c->chunk_events[chunk], c->copy_stream));
-    MFB_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_events[chunk], 0));
-    if (staged) {
-      int rc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid + o0, d->d_rating + o0, o1 - o0);
-      if (rc) return rc;
-      MFB_CUDA(cudaEventRecord(c->stage_free[sb], c->stream));
-      c->h2d_bytes += (o1 - o0) * 3;
-    } else {
-      c->h2d_bytes += (o1 - o0) * 8;
-    }
-    c->h2d_bytes += (r1 - r0) * 8 + 4;
-    int rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
-    if (rc) return rc;
+    // the update kernel of this chunk: streams alternate, each launch gets half the width
+    const bool second = two && (chunk & 1) == 0;
+    c->stream = second ? c->stream2 : main_stream;
+    c->counter_slot = second ? 2 : 0;
+    c->width_div = two ? 2 : 1;
+    cudaError_t e = cudaStreamWaitEvent(c->stream, c->chunk_events[chunk], 0);
+    if (e == cudaSuccess) rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
+    c->stream = main_stream;
+    c->counter_slot = 0;
+    c->width_div = 1;
+    MFB_CUDA(e);
     r0 = r1;
   }
+  if (rc) return rc;
+  MFB_CUDA(cudaEventRecord(c->ev_s2, c->stream2));
+  MFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_s2, 0));
   end_timing(c);
   return MFB_OK;
 }
@@ -715,11 +760,10 @@ int mfb_blocks_pin(mfb_blocks* b) {
       code[i] = (uint8_t)last_code;
     }
     if (fits) {
-      s->p_vid.resize(n);
+      MFB_CUDA(cudaHostAlloc((void**)&s->p_vid, n * sizeof(uint16_t), cudaHostAllocPortable));
+      MFB_CUDA(cudaHostAlloc((void**)&s->p_code, n, cudaHostAllocPortable));
       for (size_t i = 0; i < n; i++) s->p_vid[i] = (uint16_t)s->h_vid[i];
-      s->p_code.swap(code);
-      MFB_CUDA(reg(s->p_vid.data(), n * sizeof(uint16_t)));
-      MFB_CUDA(reg(s->p_code.data(), n));
+      memcpy(s->p_code, code.data(), n);
       s->packed = true;
     }
   }
@@ -735,10 +779,10 @@ int mfb_blocks_unpin(mfb_blocks* b) {
   if (!s->h_vid.empty()) cudaHostUnregister(s->h_vid.data());
   if (!s->h_rating.empty()) cudaHostUnregister(s->h_rating.data());
   if (s->packed) {
-    cudaHostUnregister(s->p_vid.data());
-    cudaHostUnregister(s->p_code.data());
-    std::vector<uint16_t>().swap(s->p_vid);
-    std::vector<uint8_t>().swap(s->p_code);
+    cudaFreeHost(s->p_vid);
+    cudaFreeHost(s->p_code);
+    s->p_vid = nullptr;
+    s->p_code = nullptr;
     s->packed = false;
   }
   s->pinned = false;

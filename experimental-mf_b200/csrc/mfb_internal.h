@@ -47,8 +47,8 @@ struct Dataset {
   // compact wire form of vid/rating for host -> device streaming (mfb_blocks_pin builds it when the
   // data allow: item ids below 65536 and at most 256 distinct rating values): 3 bytes per record
   // instead of 8, lossless
-  std::vector<uint16_t> p_vid;
-  std::vector<uint8_t> p_code;
+  uint16_t* p_vid = nullptr;   // cudaHostAlloc'ed (page-locked from the start)
+  uint8_t* p_code = nullptr;
   float p_dict[256] = {0};
   bool packed = false;
   // device SoA tiles
@@ -83,13 +83,17 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-streamed epochs: a second stream carries the H2D copies of the next chunk
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // second compute stream of the streamed epoch (alternating chunks)
+  cudaEvent_t ev_s2 = nullptr;
+  int counter_slot = 0;             // which int of d_counter the next epoch launch uses as its queue head
+  int width_div = 1;                // the next launch takes 1/width_div of the width the bounds allow
   std::vector<cudaEvent_t> chunk_events;
   // ... packed chunks land in one of two staging buffers and are expanded on the device
   uint16_t* d_stage_vid[2] = {nullptr, nullptr};
   uint8_t* d_stage_code[2] = {nullptr, nullptr};
   float* d_dict = nullptr;  // [256]
   int64_t stage_capacity = 0;
-  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+
   bool timed = false;
   int64_t launches = 0;
   int64_t h2d_bytes = 0;  // bytes copied host -> device by the streamed epochs since create
@@ -116,7 +120,10 @@ struct Context {
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
   double rate_stream = 1.2e6, rate_burst = 5.0e6;  // updates/s per run in flight (measured; for the choice)
-  int opt_depth = 0;            // burst kernel: batches requested ahead (1, 2; 0 = choose)
+  int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
+  int opt_epoch_launches = 1;   // diagnostic: mfb_sgd_epoch as this many launches over equal run ranges
+  int opt_tail_runs = 2;        // stream/burst kernels: runs per group handed out one by one at the end of a launch
+  int opt_depth = 1;            // burst kernel: batches requested ahead (1 or 2)
   int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the
                                 // deepest ring the budget of the hottest row leaves room for)
   int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,

@@ -396,9 +396,11 @@ __global__ void unpack_kernel(const uint16_t* __restrict__ vid16, const uint8_t*
   __shared__ float sdict[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sdict[i] = dict[i];
   __syncthreads();
+  // streaming loads and stores (evict-first): 11 bytes per record pass through here every epoch and
+  // must not push the item matrix out of the L2
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    vid[i] = vid16[i];
-    rating[i] = sdict[code[i]];
+    __stcs(vid + i, (int32_t)__ldcs(vid16 + i));
+    __stcs(rating + i, sdict[__ldcs(code + i)]);
   }
 }
 
@@ -474,7 +476,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.run_off = d->d_run_off;
   a.vid = d->d_vid;
   a.rating = d->d_rating;
-  a.counter = c->d_counter;
+  a.counter = c->d_counter + c->counter_slot;
   a.big_spans = 0;
   a.run_begin = (int)run_begin;
   a.nruns = (int)run_end;
@@ -494,7 +496,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
     MFB_CUDA(cudaStreamWaitEvent(c->stream, d->refreshed, 0));
     d->refresh_pending = false;
   }
-  MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+  MFB_CUDA(cudaMemsetAsync(c->d_counter + c->counter_slot, 0, sizeof(int), c->stream));
   // Which kernel.  The streaming sub-warp kernel needs the fewest instructions and L2 transactions
   // per update and wins when the GPU can be filled.  When the bounds on concurrency (mfb_internal.h)
   // leave only a few hundred user-runs in flight - a DSGD cell on one of many GPUs, the first

@@ -402,7 +402,7 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   // a run holds the batch being computed and the D requested ones between gather and reduction
   warps = bounded_groups(c, warps, d->max_item_share, d->nruns, (double)(D + 1) * B, a.eta);
   SgdArgs aa = a;
-  aa.big_spans = (int)std::max<int64_t>(0, (nruns - 2 * warps) / 32);  // ~2 single runs per warp at the end
+  aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * warps) / 32);  // single runs at the end
   const int nspans = aa.big_spans + (nruns - aa.big_spans * 32);
   int grid, threads;
   if (warps <= c->sm_count) {
@@ -429,15 +429,10 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
 int launch_sgd_burst(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled) {
   *handled = a.nvec > 16 && a.nvec <= 32;  // rows of 68..128 floats: one float4 per lane
   if (!*handled) return MFB_OK;
-  // depth: batches requested ahead.  2 hides the L2 latency of a loaded machine; it also holds one
-  // more batch of rows in flight per run, so when the budget of the hottest row (not the run bound)
-  // limits the launch, depth 1 keeps more runs in flight.
-  int depth = c->opt_depth;
-  if (depth == 0) {
-    const int64_t cap = (int64_t)c->sm_count * 64;
-    const int64_t run_only = bounded_groups(c, cap, 0.0, d->nruns, 1.0, a.eta);
-    depth = bounded_groups(c, cap, d->max_item_share, d->nruns, 3.0 * c->opt_batch, a.eta) >= run_only ? 2 : 1;
-  }
+  // depth: batches requested ahead.  One is enough wherever it was measured (tools/exp_wbound.py,
+  // tools/exp_e2e2.py): two ahead gains 5% per run at 210 runs in flight and loses 10% when the
+  // machine is full, and it holds one more batch of rows in flight per run.
+  const int depth = c->opt_depth == 2 ? 2 : 1;
   if (c->opt_batch == 8) return depth == 2 ? launch_burst_t<8, 2>(c, d, a, mode) : launch_burst_t<8, 1>(c, d, a, mode);
   return depth == 2 ? launch_burst_t<4, 2>(c, d, a, mode) : launch_burst_t<4, 1>(c, d, a, mode);
 }

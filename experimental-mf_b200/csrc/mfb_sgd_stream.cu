@@ -401,7 +401,7 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   int64_t subs = std::min<int64_t>(stream_capacity<LPR, VPL, R>(c, k), std::max((nruns + LPR - 1) / LPR, 1));
   subs = bounded_groups(c, subs, d->max_item_share, d->nruns, ring_weight<R>(), a.eta);
   SgdArgs aa = a;
-  aa.big_spans = (int)std::max<int64_t>(0, (nruns - 2 * subs) / LPR);  // ~2 single runs per sub-warp at the end
+  aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * subs) / LPR);  // single runs at the end
   const int nspans = aa.big_spans + (nruns - aa.big_spans * LPR);
   // spread the warps over all SMs before stacking them: 1..4 warps per CTA
   const int64_t warps = (subs + subs_per_warp - 1) / subs_per_warp;

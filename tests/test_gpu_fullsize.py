@@ -19,6 +19,17 @@ def data():
     return tr, te
 
 
+def chunk_count(run_off, base):
+    """chunks of mfb_sgd_epoch_from_host: base, then x7/4 each up to 6x base, cut at run boundaries"""
+    nruns, r0, k, want = len(run_off) - 1, 0, 0, base
+    while r0 < nruns:
+        r1 = int(np.searchsorted(run_off, run_off[r0] + want, side="right")) - 1
+        r0 = max(r1, r0 + 1)
+        k += 1
+        want = min(want * 7 // 4, 6 * base)
+    return k
+
+
 def fresh(tr, te):
     c = mb.Context(NU, NV, K)
     c.init_normal(0x4D46B200, 1e-2)
@@ -89,7 +100,7 @@ def test_streamed_epoch_equals_resident_epoch_at_full_size(data):
                 c.sgd_epoch(dtr, eta, 5e-3, GB, mb.MODE_ATOMIC)
         got.append(c.rmse(dte, GB))
         if streamed:
-            assert c.h2d_bytes() == 2 * (3 * tr.nratings + 8 * tr.nruns + 4 * 4)  # 3-byte records, 4 chunks (2+8+32+64 M)
+            assert c.h2d_bytes() == 2 * (3 * tr.nratings + 8 * tr.nruns + 4 * chunk_count(tr.run_off, 3 << 20))
         c.close()
     tr.unpin()
     assert abs(got[0] - got[1]) <= 5e-4, got
