@@ -288,6 +288,8 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "batch")) {
     MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
     c->opt_batch = value;
+  } else if (!strcmp(name, "phi_planes")) {
+    c->opt_phi_planes = value != 0;
   } else if (!strcmp(name, "two_streams")) {
     c->opt_two_streams = value != 0;
   } else if (!strcmp(name, "epoch_launches")) {

@@ -120,6 +120,7 @@ struct Context {
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
   double rate_stream = 1.2e6, rate_burst = 5.0e6;  // updates/s per run in flight (measured; for the choice)
+  int opt_phi_planes = 0;       // experiment: plane addressing of the item matrix in the stream kernel
   int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
   int opt_epoch_launches = 1;   // diagnostic: mfb_sgd_epoch as this many launches over equal run ranges
   int opt_tail_runs = 2;        // stream/burst kernels: runs per group handed out one by one at the end of a launch

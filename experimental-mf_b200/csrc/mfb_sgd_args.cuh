@@ -20,6 +20,10 @@ struct SgdArgs {
   // stream/burst kernels: the first big_spans spans are full (LPR resp. 32 consecutive runs), the runs
   // after them are handed out one by one, so that the kernel's tail is one run long, not one span
   int big_spans;
+  // stream kernel: float4 index of (item v, this lane's vector i) = v*phi_row4 + i*phi_line4 + lane.
+  // Rows as they are: (nvec, LPR).  Plane layout: (LPR, planes of nv*LPR float4) - the 128-byte lines
+  // of one row then lie nv*128 bytes apart and hash to different L2 slices.
+  int64_t phi_row4, phi_line4;
   float eta, lameta, lm1, gb;
   int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
   int throttle;  // streaming kernel: wait for the previous record's bias atomic before the next reductions

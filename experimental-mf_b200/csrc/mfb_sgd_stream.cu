@@ -177,10 +177,10 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
       const int v = lds1i(chunk0 + cbuf * 256 + (sub * LPR + idx) * 4);
       fr[s] = lds1(chunk0 + cbuf * 256 + 128 + (sub * LPR + idx) * 4);
       fv[s] = v;
-      const float4* p = phi4 + (int64_t)v * a.nvec + gl;
+      const float4* p = phi4 + (int64_t)v * a.phi_row4 + gl;
 #pragma unroll
       for (int i = 0; i < VPL; i++)
-        if (ok[i]) cp_async16(ring_me + (s * 32 * VPL + i * LPR) * 16, p + i * LPR);
+        if (ok[i]) cp_async16(ring_me + (s * 32 * VPL + i * LPR) * 16, p + i * a.phi_line4);
       // the 16 aligned bytes around bv[v] (4-byte cp.async would go through L1, which is not coherent)
       if (gl == 0) cp_async16(bias_sub + s * SM::SUBS * 16, a.bv + (v & ~3));
       if (a.version) fver[s] = __ldcg(a.version + v);
@@ -318,17 +318,17 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
         // while the L2 keeps up (the round trip overlaps a whole step).
         if (a.throttle) sink ^= __float_as_uint(ack[u & 1]);
         // the reductions come first: they end the window in which this row is stale elsewhere
-        float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)fv[s] * a.nvec + gl;
+        float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)fv[s] * a.phi_row4 + gl;
         const float2 keep = (MODE == MFB_MODE_ATOMIC) ? lm12 : lameta2;  // increment vs new value
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
           const float4 nf = cat4(__ffma2_rn(e2, lo2(t[i]), __fmul2_rn(keep, lo2(f[i]))),
                                  __ffma2_rn(e2, hi2(t[i]), __fmul2_rn(keep, hi2(f[i]))));
           if (MODE == MFB_MODE_ATOMIC) {
-            if (EXACT) red_add4(dst + i * LPR, nf);
-            else red_add4p(dst + i * LPR, nf, ok[i]);
+            if (EXACT) red_add4(dst + i * a.phi_line4, nf);
+            else red_add4p(dst + i * a.phi_line4, nf, ok[i]);
           } else if (ok[i]) {
-            __stcg(dst + i * LPR, nf);
+            __stcg(dst + i * a.phi_line4, nf);
           }
         }
         if (gl == 0) ack[u & 1] = atom_add1(a.bv + fv[s], fmaf(a.lm1, bvv, e));
@@ -402,6 +402,12 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   subs = bounded_groups(c, subs, d->max_item_share, d->nruns, ring_weight<R>(), a.eta);
   SgdArgs aa = a;
   aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * subs) / LPR);  // single runs at the end
+  aa.phi_row4 = a.nvec;
+  aa.phi_line4 = LPR;
+  if (c->opt_phi_planes && a.nvec == LPR * VPL) {  // EXPERIMENT: plane addressing without transposing the data
+    aa.phi_row4 = LPR;
+    aa.phi_line4 = (int64_t)c->nv * LPR;
+  }
   const int nspans = aa.big_spans + (nruns - aa.big_spans * LPR);
   // spread the warps over all SMs before stacking them: 1..4 warps per CTA
   const int64_t warps = (subs + subs_per_warp - 1) / subs_per_warp;
