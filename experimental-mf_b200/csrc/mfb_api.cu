@@ -295,6 +295,9 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "epoch_launches")) {
     MFB_REQUIRE(value >= 1 && value <= 4096, "epoch_launches out of range");
     c->opt_epoch_launches = value;
+  } else if (!strcmp(name, "span_runs")) {
+    MFB_REQUIRE(value >= 0 && value <= 32, "span_runs must be 0..32");
+    c->opt_span_runs = value;
   } else if (!strcmp(name, "tail_runs")) {
     MFB_REQUIRE(value >= 0 && value <= 1024, "tail_runs out of range");
     c->opt_tail_runs = value;

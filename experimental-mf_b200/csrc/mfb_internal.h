@@ -123,6 +123,7 @@ struct Context {
   int opt_phi_planes = 0;       // experiment: plane addressing of the item matrix in the stream kernel
   int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
   int opt_epoch_launches = 1;   // diagnostic: mfb_sgd_epoch as this many launches over equal run ranges
+  int opt_span_runs = 0;        // burst kernel: runs per claim (0 = by file size: 8, 16 or 32)
   int opt_tail_runs = 2;        // stream/burst kernels: runs per group handed out one by one at the end of a launch
   int opt_depth = 1;            // burst kernel: batches requested ahead (1 or 2)
   int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the

@@ -478,6 +478,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   a.rating = d->d_rating;
   a.counter = c->d_counter + c->counter_slot;
   a.big_spans = 0;
+  a.span_runs = 32;
   a.run_begin = (int)run_begin;
   a.nruns = (int)run_end;
   a.nvec = c->stride / 4;
@@ -506,7 +507,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   if (c->opt_kernel == 0) {
     c->use_kernel = 3;
     const int nvec = a.nvec;
-    if (mode != MFB_MODE_ORDERED && nvec > 16 && nvec <= 32) {
+    if (mode != MFB_MODE_ORDERED && nvec <= 32) {
       const int64_t runs = a.nruns - a.run_begin;
       const int64_t cap = (int64_t)c->sm_count * 64;  // more than either kernel holds: bounds only
       const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 0.6, eta), runs);

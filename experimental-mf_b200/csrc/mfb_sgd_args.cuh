@@ -20,6 +20,7 @@ struct SgdArgs {
   // stream/burst kernels: the first big_spans spans are full (LPR resp. 32 consecutive runs), the runs
   // after them are handed out one by one, so that the kernel's tail is one run long, not one span
   int big_spans;
+  int span_runs;  // burst kernel: runs per claim (<= 32)
   // stream kernel: float4 index of (item v, this lane's vector i) = v*phi_row4 + i*phi_line4 + lane.
   // Rows as they are: (nvec, LPR).  Plane layout: (LPR, planes of nv*LPR float4) - the 128-byte lines
   // of one row then lie nv*128 bytes apart and hash to different L2 slices.

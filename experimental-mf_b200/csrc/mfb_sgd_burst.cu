@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     if (lane0) sp = atomicAdd(a.counter, 1);
     sp = __shfl_sync(FULL, sp, 0);
     if (sp >= nspans) break;
-    int run0 = a.run_begin + sp * 32, span_n = 32;
+    int run0 = a.run_begin + sp * a.span_runs, span_n = a.span_runs;
     if (sp >= a.big_spans) {  // the tail of the launch: single runs
-      run0 = a.run_begin + a.big_spans * 32 + (sp - a.big_spans);
+      run0 = a.run_begin + a.big_spans * a.span_runs + (sp - a.big_spans);
       span_n = 1;
     }
     int s_uid = 0, s_end = 0;  // per lane: user and record-end of run `lane` of the span
@@ -398,12 +398,16 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   MFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * WARP_BYTES));
   per_sm = std::max(per_sm, 1);
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-  int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max((nruns + 31) / 32, 1));
+  // runs per claim: 32, fewer when the file is small - the claims in flight then cover a shorter
+  // stretch of the file and the order of updates stays closer to the file order
+  const int span_runs = c->opt_span_runs > 0 ? c->opt_span_runs : (d->nruns >= 400000 ? 32 : (d->nruns >= 100000 ? 16 : 8));
+  int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max((nruns + span_runs - 1) / span_runs, 1));
   // a run holds the batch being computed and the D requested ones between gather and reduction
   warps = bounded_groups(c, warps, d->max_item_share, d->nruns, (double)(D + 1) * B, a.eta);
   SgdArgs aa = a;
-  aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * warps) / 32);  // single runs at the end
-  const int nspans = aa.big_spans + (nruns - aa.big_spans * 32);
+  aa.span_runs = span_runs;
+  aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * warps) / span_runs);  // single runs at the end
+  const int nspans = aa.big_spans + (nruns - aa.big_spans * span_runs);
   int grid, threads;
   if (warps <= c->sm_count) {
     grid = (int)warps;
@@ -427,7 +431,9 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
 }  // namespace
 
 int launch_sgd_burst(Context* c, const Dataset* d, const SgdArgs& a, int mode, bool* handled) {
-  *handled = a.nvec > 16 && a.nvec <= 32;  // rows of 68..128 floats: one float4 per lane
+  // rows of up to 128 floats: one float4 per lane; shorter rows leave lanes idle, which costs nothing
+  // where this kernel is used (few runs in flight, latency of a single run's chain is what counts)
+  *handled = a.nvec <= 32;
   if (!*handled) return MFB_OK;
   // depth: batches requested ahead.  One is enough wherever it was measured (tools/exp_wbound.py,
   // tools/exp_e2e2.py): two ahead gains 5% per run at 210 runs in flight and loses 10% when the

@@ -305,7 +305,7 @@ def test_staleness_probe_counts_every_update_and_sees_no_staleness_when_serial()
 
 def test_kernel_choice_follows_the_concurrency_bounds():
     """Auto choice (kernel = 0): a launch the bounds keep narrow goes to the burst kernel, a wide one
-    to the stream kernel; rows outside 68..128 floats always to the stream kernel."""
+    to the stream kernel; rows longer than 128 floats always to the stream kernel."""
     nu, nv = 20000, 2000
     tr, _, _ = mb.generate(mb.gen_params(nu, nv, 1_000_000, test_frac=0.0))
     c = mb.Context(nu, nv, 128)
@@ -318,9 +318,10 @@ def test_kernel_choice_follows_the_concurrency_bounds():
     c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)
     assert c.last_launch()["kernel"] == 3
     c.close()
-    c = mb.Context(nu, nv, 32)
-    c.init_normal(1, 1e-2)
-    d = c.dataset_from_blocks(tr)
-    c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)
-    assert c.last_launch()["kernel"] == 3
-    c.close()
+    for dim, want in ((32, 4), (256, 3)):
+        c = mb.Context(nu, nv, dim)
+        c.init_normal(1, 1e-2)
+        d = c.dataset_from_blocks(tr)
+        c.sgd_epoch(d, 0.02, 5e-3, GB, mb.MODE_ATOMIC)
+        assert c.last_launch()["kernel"] == want
+        c.close()
