@@ -14,6 +14,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 namespace mfb {
 namespace {
 
@@ -187,27 +192,132 @@ int for_each_frame(const char* path, const std::function<bool(const void*, size_
   return rc;
 }
 
+// Parse a whole file: the frame boundaries come from one sequential walk over the length prefixes
+// (a jump per frame), the frames are decoded by worker threads (the reference decodes one Block
+// per ParseFilter call on a TBB worker, mf.h:57-69, and does so again every epoch; here it happens
+// once), and the per-frame results are stitched together in file order.
 int load_blocks_file(const char* path, Dataset* d) {
   if (d->h_run_off.empty()) d->h_run_off.push_back(0);
   if (d->h_block_off.empty()) d->h_block_off.push_back(0);
-  BlockSink sink;
-  return for_each_frame(path, [&](const void* data, size_t size) {
-    sink.uid.clear();
-    sink.vid.clear();
-    sink.rating.clear();
-    sink.rec_off.assign(1, 0);
-    if (!decode_block(data, size, &sink)) return false;
-    const int64_t base = (int64_t)d->h_vid.size();
-    if (base + (int64_t)sink.vid.size() >= (int64_t)INT32_MAX) return false;
-    for (size_t i = 0; i < sink.uid.size(); i++) {
-      d->h_run_uid.push_back(sink.uid[i]);
-      d->h_run_off.push_back((int32_t)(base + sink.rec_off[i + 1]));
+  struct Frame {
+    const void* data;
+    size_t size;
+  };
+  std::vector<Frame> frames;
+  // for_each_frame unmaps the file when it returns, so the decoding happens inside the callback of a
+  // second walk; the first walk only counts (cheap: one 4-byte read per frame)
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    set_error("cannot open %s", path);
+    return MFB_E_IO;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    set_error("cannot stat %s", path);
+    return MFB_E_IO;
+  }
+  const size_t size = (size_t)st.st_size;
+  if (size == 0) {
+    close(fd);
+    return MFB_OK;
+  }
+  void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) {
+    set_error("cannot mmap %s", path);
+    return MFB_E_IO;
+  }
+  const uint8_t* p = (const uint8_t*)map;
+  const uint8_t* end = p + size;
+  while (end - p >= 4) {  // util.h:81 `while(fread(&isize, 1, sizeof(isize), fr))`
+    uint32_t isize;
+    memcpy(&isize, p, 4);
+    p += 4;
+    if ((size_t)(end - p) < isize) {
+      set_error("%s: truncated frame (%u bytes wanted, %zu left)", path, isize, (size_t)(end - p));
+      munmap(map, size);
+      return MFB_E_IO;
     }
-    d->h_vid.insert(d->h_vid.end(), sink.vid.begin(), sink.vid.end());
-    d->h_rating.insert(d->h_rating.end(), sink.rating.begin(), sink.rating.end());
-    d->h_block_off.push_back((int64_t)d->h_run_uid.size());
-    return true;
-  });
+    frames.push_back(Frame{p, isize});
+    p += isize;
+  }
+  const size_t nf = frames.size();
+  std::vector<BlockSink> sinks(nf);
+  std::vector<char> ok(nf, 1);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nthreads = std::min<size_t>(hw, std::max<size_t>(1, nf / 4));
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nf) break;
+      sinks[i].rec_off.assign(1, 0);
+      ok[i] = decode_block(frames[i].data, frames[i].size, &sinks[i]) ? 1 : 0;
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+  }
+  int rc = MFB_OK;
+  int64_t total = (int64_t)d->h_vid.size(), runs = (int64_t)d->h_run_uid.size();
+  for (size_t i = 0; i < nf && rc == MFB_OK; i++) {
+    if (!ok[i]) {
+      set_error("%s: malformed mf.Block at offset %zu", path, (size_t)((const uint8_t*)frames[i].data - (const uint8_t*)map));
+      rc = MFB_E_IO;
+    }
+    total += (int64_t)sinks[i].vid.size();
+    runs += (int64_t)sinks[i].uid.size();
+    if (total >= (int64_t)INT32_MAX) {
+      set_error("%s: more than 2^31 records", path);
+      rc = MFB_E_IO;
+    }
+  }
+  munmap(map, size);
+  if (rc) return rc;
+  // stitch: offsets by prefix sum, payload copied by the same workers
+  std::vector<int64_t> rec0(nf + 1), run0(nf + 1);
+  rec0[0] = (int64_t)d->h_vid.size();
+  run0[0] = (int64_t)d->h_run_uid.size();
+  for (size_t i = 0; i < nf; i++) {
+    rec0[i + 1] = rec0[i] + (int64_t)sinks[i].vid.size();
+    run0[i + 1] = run0[i] + (int64_t)sinks[i].uid.size();
+  }
+  d->h_vid.resize(rec0[nf]);
+  d->h_rating.resize(rec0[nf]);
+  d->h_run_uid.resize(run0[nf]);
+  d->h_run_off.resize(run0[nf] + 1);
+  const size_t blocks0 = d->h_block_off.size();
+  d->h_block_off.resize(blocks0 + nf);
+  next = 0;
+  auto stitch = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nf) break;
+      const BlockSink& b = sinks[i];
+      if (!b.vid.empty()) {
+        memcpy(d->h_vid.data() + rec0[i], b.vid.data(), b.vid.size() * sizeof(int32_t));
+        memcpy(d->h_rating.data() + rec0[i], b.rating.data(), b.rating.size() * sizeof(float));
+      }
+      for (size_t k = 0; k < b.uid.size(); k++) {
+        d->h_run_uid[run0[i] + k] = b.uid[k];
+        d->h_run_off[run0[i] + k + 1] = (int32_t)(rec0[i] + b.rec_off[k + 1]);
+      }
+      d->h_block_off[blocks0 + i] = run0[i + 1];
+      std::vector<int32_t>().swap(sinks[i].vid);
+      std::vector<float>().swap(sinks[i].rating);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(stitch);
+    stitch();
+    for (auto& t : pool) t.join();
+  }
+  return MFB_OK;
 }
 
 }  // namespace mfb
