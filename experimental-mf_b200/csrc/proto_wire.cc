@@ -19,6 +19,9 @@
 #include <thread>
 #include <vector>
 
+#include <chrono>
+#define TIMER_T0 auto _t0 = std::chrono::steady_clock::now()
+#define TIMER_LAP(name) do { auto _t1 = std::chrono::steady_clock::now(); if (getenv("MFB_TIMING")) fprintf(stderr, "load_blocks_file %s %.3f s\n", name, std::chrono::duration<double>(_t1 - _t0).count()); _t0 = _t1; } while (0)
 namespace mfb {
 namespace {
 
@@ -65,6 +68,8 @@ struct Cursor {
 
 bool decode_block(const void* data, size_t size, BlockSink* out) {
   Cursor blk{(const uint8_t*)data, (const uint8_t*)data + size, true};
+  out->vid.reserve(out->vid.size() + size / 9);  // a record takes at least 9 bytes on the wire
+  out->rating.reserve(out->rating.size() + size / 9);
   while (blk.more()) {
     const uint64_t tag = blk.varint();
     if (tag != 0x0A) {
@@ -77,6 +82,30 @@ bool decode_block(const void* data, size_t size, BlockSink* out) {
     out->uid.push_back(0);
     const size_t slot = out->uid.size() - 1;
     while (usr.more()) {
+      // Fast path for the canonical record protobuf's encoder writes (blocks.pb.cc:267,281):
+      // 12 LL 08 <vid varint, 1..3 bytes> 15 <4 bytes>; anything else goes the general way below.
+      if (usr.end - usr.p >= 11 && usr.p[0] == 0x12 && usr.p[2] == 0x08) {
+        const uint8_t* q = usr.p;
+        const uint32_t len = q[1];
+        uint32_t v = q[3];
+        uint32_t vl = 1;
+        if (v & 0x80) {
+          v = (v & 0x7F) | ((uint32_t)q[4] << 7);
+          vl = 2;
+          if (v & (0x80u << 7)) {
+            v = (v & 0x3FFF) | ((uint32_t)q[5] << 14);
+            vl = 3;
+          }
+        }
+        if (len == vl + 6 && !(v & (0x80u << (7 * (vl - 1)))) && q[3 + vl] == 0x15) {
+          float rating;
+          memcpy(&rating, q + 4 + vl, 4);
+          out->vid.push_back((int32_t)v);
+          out->rating.push_back(rating);
+          usr.p = q + 2 + len;
+          continue;
+        }
+      }
       const uint64_t t = usr.varint();
       if (t == 0x08) {
         uid = (int32_t)(uint32_t)usr.varint();
@@ -243,6 +272,7 @@ int load_blocks_file(const char* path, Dataset* d) {
     p += isize;
   }
   const size_t nf = frames.size();
+  TIMER_T0;
   std::vector<BlockSink> sinks(nf);
   std::vector<char> ok(nf, 1);
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -262,6 +292,7 @@ int load_blocks_file(const char* path, Dataset* d) {
     worker();
     for (auto& t : pool) t.join();
   }
+  TIMER_LAP("decode");
   int rc = MFB_OK;
   int64_t total = (int64_t)d->h_vid.size(), runs = (int64_t)d->h_run_uid.size();
   for (size_t i = 0; i < nf && rc == MFB_OK; i++) {
@@ -286,12 +317,37 @@ int load_blocks_file(const char* path, Dataset* d) {
     rec0[i + 1] = rec0[i] + (int64_t)sinks[i].vid.size();
     run0[i + 1] = run0[i] + (int64_t)sinks[i].uid.size();
   }
+  TIMER_LAP("check+munmap");
+  // first touch of the two big arrays by all threads (a serial resize() spends more time in page
+  // faults than the whole decode): reserve, pre-fault the reserved pages in parallel, then resize
+  d->h_vid.reserve(rec0[nf]);
+  d->h_rating.reserve(rec0[nf]);
+  {
+    auto prefault = [&](void* base, size_t bytes, size_t t) {
+      const uintptr_t lo = ((uintptr_t)base + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)base + bytes) & ~(uintptr_t)4095;
+      if (hi <= lo) return;
+      const size_t pages = (hi - lo) >> 12, p0 = pages * t / nthreads, p1 = pages * (t + 1) / nthreads;
+#ifdef MADV_POPULATE_WRITE
+      if (p1 > p0) madvise((void*)(lo + (p0 << 12)), (p1 - p0) << 12, MADV_POPULATE_WRITE);  // best effort
+#endif
+    };
+    auto job = [&](size_t t) {
+      prefault(d->h_vid.data(), (size_t)rec0[nf] * sizeof(int32_t), t);
+      prefault(d->h_rating.data(), (size_t)rec0[nf] * sizeof(float), t);
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(job, t);
+    job(0);
+    for (auto& t : pool) t.join();
+  }
+  TIMER_LAP("prefault");
   d->h_vid.resize(rec0[nf]);
   d->h_rating.resize(rec0[nf]);
   d->h_run_uid.resize(run0[nf]);
   d->h_run_off.resize(run0[nf] + 1);
   const size_t blocks0 = d->h_block_off.size();
   d->h_block_off.resize(blocks0 + nf);
+  TIMER_LAP("resize");
   next = 0;
   auto stitch = [&]() {
     for (;;) {
@@ -317,6 +373,7 @@ int load_blocks_file(const char* path, Dataset* d) {
     stitch();
     for (auto& t : pool) t.join();
   }
+  TIMER_LAP("stitch");
   return MFB_OK;
 }
 
