@@ -66,50 +66,97 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
+    (about a millisecond per sample, so even a 50 ms region gets tens of samples); nvidia-smi -lms
+    as the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop_flag, self.t = None, None, False, None
+        self.source = None
+
+    def _nvml_index(self):
+        # LOCAL_RANK counts visible devices; NVML counts physical ones
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         if os.environ.get("MFB_NO_SAMPLER"):
             return
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                  "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, self.max_mhz, [name for bit, name in bits if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                self.rows.append((float(r[0]), float(r[1]),
+                                  [name for name, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+
+    def stop(self):
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML and no nvidia-smi"]}
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons.update(r[2])
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------ CPU arm

@@ -9,27 +9,36 @@
 //   counter = ( t , row , chunk , kind + 2*round ),  key = ( seed_lo , seed_hi )
 //   t     : logical clock of the rating in the epoch (dpmf.h:62 `gc`); ntrain for finish_noise
 //   row   : user or item index;  kind : 0 = user row, 1 = item row
-//   chunk : coordinate/4 for the factor row, MFB_BIAS_CHUNK for the bias term (value [0] used)
-// The 4 outputs become 4 normals by two Box-Muller transforms on 24-bit uniforms.
+//   chunk : coordinate/4 for the factor row
+// The 4 outputs become 4 normals by two Box-Muller transforms on the TOP 24 bits of each word.
+// The bias term of the same (kind,row,t) is made from the bits those transforms leave unused: the
+// low bytes of words x,y,z of chunk 0 form the 24-bit u1 and those of chunk 1 the 24-bit u2
+// (spare_bits24 / box_muller_bias), so the bias costs no Philox evaluation of its own - it was a
+// third of the generator work of a record (chunks 0 and 1 are evaluated by lanes 0 and 1 anyway).
 #ifndef MFB_PHILOX_CUH
 #define MFB_PHILOX_CUH
 
 #include <stdint.h>
-
-#define MFB_BIAS_CHUNK 0x7FFFFFFFu
 
 namespace mfb {
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    // one IMAD.WIDE.U32 per product (hi and lo halves together): 20 multiplies per call, not 40
+    uint32_t hi0, lo0, hi1, lo1;
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p; }" : "=r"(lo0), "=r"(hi0) : "r"(c.x), "r"(0xD2511F53u));
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p; }" : "=r"(lo1), "=r"(hi1) : "r"(c.z), "r"(0xCD9E8D57u));
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
     k.x += 0x9E3779B9u;
     k.y += 0xBB67AE85u;
   }
   return c;
+}
+
+// the 24 bits of a Philox block that box_muller4 does not use: low bytes of words x, y, z
+__device__ __forceinline__ uint32_t spare_bits24(uint4 x) {
+  return (x.x & 0xFFu) | ((x.y & 0xFFu) << 8) | ((x.z & 0xFFu) << 16);
 }
 
 // u1 = ((x>>8)+1)/2^24 in (0,1], u2 = (x>>8)/2^24 in [0,1); z = sqrt(-2 ln u1) * (cos, sin)(2 pi u2)
@@ -44,17 +53,32 @@ __device__ __forceinline__ float4 box_muller4(uint4 x) {
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
-// same transform with the hardware approximations (MUFU lg2 / sin / cos): used by the Hogwild
-// kernels, where noise parity is statistical.  |error| ~ 1e-6, far below the noise itself.
-__device__ __forceinline__ float4 box_muller4_fast(uint4 x) {
+// bias normal from the spare bits of chunks 0 and 1: u1 = (s0+1)/2^24, u2 = s1/2^24, z = r cos
+__device__ __forceinline__ float box_muller_bias(uint32_t s0, uint32_t s1) {
   const float s = 1.0f / 16777216.0f;
-  const float u1 = ((float)(x.x >> 8) + 1.0f) * s, u2 = (float)(x.y >> 8) * s;
-  const float u3 = ((float)(x.z >> 8) + 1.0f) * s, u4 = (float)(x.w >> 8) * s;
-  const float r0 = sqrtf(-2.0f * __logf(u1)), r1 = sqrtf(-2.0f * __logf(u3));
-  float s0, c0, s1, c1;
-  __sincosf(6.28318530717958647692f * u2, &s0, &c0);
-  __sincosf(6.28318530717958647692f * u4, &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+  const float u1 = ((float)s0 + 1.0f) * s, u2 = (float)s1 * s;
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+}
+
+// same transforms with the hardware approximations (MUFU lg2 / sqrt / sin / cos, one instruction each):
+// used by the Hogwild kernels, where noise parity is statistical.  |error| ~ 1e-6, far below the
+// noise itself.  sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u).
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float4 box_muller4_fast(uint4 x) {
+  const float s = 1.0f / 16777216.0f, w = 6.28318530717958647692f / 16777216.0f;
+  const float u1 = ((float)(x.x >> 8) + 1.0f) * s, a0 = (float)(x.y >> 8) * w;
+  const float u3 = ((float)(x.z >> 8) + 1.0f) * s, a1 = (float)(x.w >> 8) * w;
+  const float r0 = mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u1));
+  const float r1 = mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u3));
+  return make_float4(r0 * mufu_cos(a0), r0 * mufu_sin(a0), r1 * mufu_cos(a1), r1 * mufu_sin(a1));
+}
+__device__ __forceinline__ float box_muller_bias_fast(uint32_t s0, uint32_t s1) {
+  const float u1 = ((float)s0 + 1.0f) * (1.0f / 16777216.0f);
+  return mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u1)) * mufu_cos((float)s1 * (6.28318530717958647692f / 16777216.0f));
 }
 
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t round, int kind,

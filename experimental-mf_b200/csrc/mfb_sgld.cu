@@ -47,16 +47,17 @@ struct SgldArgs {
   int table_offset;
 };
 
-// dim+1 noise values for (kind,row) at logical time t: factor part as a Row, bias part returned
+// dim+1 noise values for (kind,row) at logical time t: factor part as a Row, bias part returned.
+// *spare = the unused low bytes of this lane's chunk gl (i = 0), the raw material of the bias value.
 template <int LPR, int VPL, bool FAST>
-__device__ __forceinline__ Row<VPL> noise_row(const SgldArgs& a, int kind, int row, int t, int gl,
-                                              float* bias_noise) {
+__device__ __forceinline__ Row<VPL> noise_chunks(const SgldArgs& a, int kind, int row, int t, int gl, uint32_t* spare) {
   Row<VPL> z;
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
     const int v = gl + i * LPR;
     const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)row, (uint32_t)v, (uint32_t)kind + 2u * a.round),
                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    if (i == 0) *spare = spare_bits24(x);
     z.v[i] = FAST ? box_muller4_fast(x) : box_muller4(x);
     // coordinates >= dim are padding: keep them exactly zero
     const int c = 4 * v;
@@ -65,33 +66,42 @@ __device__ __forceinline__ Row<VPL> noise_row(const SgldArgs& a, int kind, int r
     if (c + 2 >= a.dim) z.v[i].z = 0.f;
     if (c + 3 >= a.dim) z.v[i].w = 0.f;
   }
-  // the bias value: chunk MFB_BIAS_CHUNK of the same (kind,row,t) stream, evaluated by lane 0 and
+  return z;
+}
+
+template <int LPR, int VPL, bool FAST>
+__device__ __forceinline__ Row<VPL> noise_row(const SgldArgs& a, int kind, int row, int t, int gl,
+                                              float* bias_noise) {
+  static_assert(LPR >= 2, "the bias value needs the chunks of lanes 0 and 1");
+  uint32_t spare;
+  const Row<VPL> z = noise_chunks<LPR, VPL, FAST>(a, kind, row, t, gl, &spare);
+  // the bias value: spare bits of chunk 0 (lane 0) and chunk 1 (lane 1), evaluated by lane 0 and
   // handed to every lane of the group (all of them carry the bias)
   if (bias_noise) {
+    const uint32_t s1 = __shfl_sync(group_mask<LPR>(), spare, 1, LPR);
     float b = 0.f;
-    if (gl == 0) {
-      const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)row, MFB_BIAS_CHUNK, (uint32_t)kind + 2u * a.round),
-                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-      b = (FAST ? box_muller4_fast(x) : box_muller4(x)).x;
-    }
+    if (gl == 0) b = FAST ? box_muller_bias_fast(spare, s1) : box_muller_bias(spare, s1);
     *bias_noise = __shfl_sync(group_mask<LPR>(), b, 0, LPR);
   }
   return z;
 }
 
 // Both rows of one record: user noise (kind 0, row uid) and item noise (kind 1, row v) at logical time
-// t.  The two bias values are evaluated in ONE pass - lane 0 the user's, lane 1 the item's - instead
-// of two passes that keep 31 lanes idle each.
+// t.  The two bias values come from the spare bits of chunks 0 and 1 of either stream and are
+// evaluated in ONE pass - lane 0 the user's, lane 1 the item's - after one exchange between the two
+// lanes (lane 0 lacks the user's chunk 1, lane 1 the item's chunk 0).
 template <int LPR, int VPL, bool FAST>
 __device__ __forceinline__ void noise_pair(const SgldArgs& a, int uid, int v, int t, int gl, unsigned m,
                                            Row<VPL>& xu, Row<VPL>& xv, float* xbu, float* xbv) {
-  xu = noise_row<LPR, VPL, FAST>(a, 0, uid, t, gl, nullptr);
-  xv = noise_row<LPR, VPL, FAST>(a, 1, v, t, gl, nullptr);
+  static_assert(LPR >= 2, "the bias values need the chunks of lanes 0 and 1");
+  uint32_t su, sv;
+  xu = noise_chunks<LPR, VPL, FAST>(a, 0, uid, t, gl, &su);
+  xv = noise_chunks<LPR, VPL, FAST>(a, 1, v, t, gl, &sv);
+  const uint32_t other = __shfl_xor_sync(m, gl == 0 ? sv : su, 1, LPR);
   float b = 0.f;
   if (gl < 2) {
-    const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(gl ? v : uid), MFB_BIAS_CHUNK, (uint32_t)gl + 2u * a.round),
-                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-    b = (FAST ? box_muller4_fast(x) : box_muller4(x)).x;
+    const uint32_t s0 = gl == 0 ? su : other, s1 = gl == 0 ? other : sv;
+    b = FAST ? box_muller_bias_fast(s0, s1) : box_muller_bias(s0, s1);
   }
   *xbu = __shfl_sync(m, b, 0, LPR);
   *xbv = __shfl_sync(m, b, 1, LPR);
@@ -209,7 +219,9 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
       if (!ORDERED && b + 1 < LPR && j + 1 < hi) fetch(b + 1);  // (items of one run are distinct)
       const float av = -a.eta * vr * a.bound;                                     // dpmf.h:81
       const double cbv = 1.0 - (double)(a.eta * a.lambda_vb * vr * a.bound);      // dpmf.h:85
-      const float su = sqrtf(a.temp * a.eta * uc), sv = sqrtf(a.temp * a.eta * vc);  // dpmf.h:67-70
+      // dpmf.h:67-70; the parallel schedule takes the square roots with one MUFU each
+      const float su = ORDERED ? sqrtf(a.temp * a.eta * uc) : mufu_sqrt(a.temp * a.eta * uc);
+      const float sv = ORDERED ? sqrtf(a.temp * a.eta * vc) : mufu_sqrt(a.temp * a.eta * vc);
       float xbu, xbv;
       Row<VPL> xu, xv;
       if (a.table) {  // dpmf.h:53-54,87 with every offset == table_offset
@@ -276,8 +288,8 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
           t.v[i] = tt;
           f.v[i] = ff;
         }
-        bu = (float)(cbu * (double)bu + (double)e);
-        bvv = (float)(cbv * (double)bvv + (double)e);
+        bu = fmaf((float)cbu, bu, e);   // (the ordered schedule keeps the reference's double arithmetic)
+        bvv = fmaf(1.0f - a.eta * a.lambda_vb * vr * a.bound, bvv, e);
       }
       if (ORDERED) {
         store_row<LPR, VPL>(a.phi, v, a.nvec, gl, f);

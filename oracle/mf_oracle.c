@@ -365,16 +365,19 @@ void mfo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-#define MFO_BIAS_CHUNK 0x7FFFFFFFu
-
 /* DESIGN.md "SGLD noise stream": counter = (t, row, chunk, kind + 2*round), key = seed.
- * Box-Muller on 24-bit uniforms: u1 = ((x>>8)+1)/2^24 in (0,1], u2 = (x>>8)/2^24 in [0,1). */
-void mfo_philox_normal4(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t,
-                        uint32_t chunk, float out[4]) {
+ * Box-Muller on the top 24 bits of each word: u1 = ((x>>8)+1)/2^24 in (0,1], u2 = (x>>8)/2^24 in [0,1). */
+static void philox_block(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t,
+                         uint32_t chunk, uint32_t x[4]) {
   uint32_t ctr[4] = {(uint32_t)t, (uint32_t)row, chunk, (uint32_t)kind + 2u * round};
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-  uint32_t x[4];
   mfo_philox4x32_10(ctr, key, x);
+}
+
+void mfo_philox_normal4(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t,
+                        uint32_t chunk, float out[4]) {
+  uint32_t x[4];
+  philox_block(seed, round, kind, row, t, chunk, x);
   for (int p = 0; p < 2; p++) {
     float u1 = ((float)(x[2 * p] >> 8) + 1.0f) * (1.0f / 16777216.0f);
     float u2 = (float)(x[2 * p + 1] >> 8) * (1.0f / 16777216.0f);
@@ -383,6 +386,19 @@ void mfo_philox_normal4(uint64_t seed, uint32_t round, int kind, int32_t row, in
     out[2 * p] = rad * cosf(ang);
     out[2 * p + 1] = rad * sinf(ang);
   }
+}
+
+/* The bias value of (kind,row,t) is made from the bits the transforms above leave unused: the low
+ * bytes of words 0..2 of chunk 0 are the 24-bit u1, those of chunk 1 the 24-bit u2; z = r cos. */
+float mfo_philox_bias_normal(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t) {
+  uint32_t x0[4], x1[4];
+  philox_block(seed, round, kind, row, t, 0u, x0);
+  philox_block(seed, round, kind, row, t, 1u, x1);
+  uint32_t s0 = (x0[0] & 0xFFu) | ((x0[1] & 0xFFu) << 8) | ((x0[2] & 0xFFu) << 16);
+  uint32_t s1 = (x1[0] & 0xFFu) | ((x1[1] & 0xFFu) << 8) | ((x1[2] & 0xFFu) << 16);
+  float u1 = ((float)s0 + 1.0f) * (1.0f / 16777216.0f);
+  float u2 = (float)s1 * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
 }
 
 void mfo_noise_from_philox(void* ctx, int kind, int32_t row, int64_t t, int32_t j, int32_t dim,
@@ -394,8 +410,7 @@ void mfo_noise_from_philox(void* ctx, int kind, int32_t row, int64_t t, int32_t 
     mfo_philox_normal4(ph->seed, ph->round, kind, row, t, (uint32_t)(c / 4), z);
     for (int i = 0; i < 4 && c + i < dim; i++) out[c + i] = z[i];
   }
-  mfo_philox_normal4(ph->seed, ph->round, kind, row, t, MFO_BIAS_CHUNK, z);
-  out[dim] = z[0];
+  out[dim] = mfo_philox_bias_normal(ph->seed, ph->round, kind, row, t);
 }
 
 /* SgldFilter::operator(), dpmf.h:41-91 */

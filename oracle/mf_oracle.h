@@ -109,6 +109,8 @@ void mfo_noise_from_philox(void* ctx, int kind, int32_t row, int64_t t, int32_t 
 /* the 4 normals of one Philox block (exposed for the known-answer / moment tests) */
 void mfo_philox_normal4(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t,
                         uint32_t chunk, float out[4]);
+/* the bias normal of (kind,row,t): Box-Muller on the low bytes of chunks 0 and 1 (mf_oracle.c) */
+float mfo_philox_bias_normal(uint64_t seed, uint32_t round, int kind, int32_t row, int64_t t);
 
 /* model.cc:240-242 */
 float mfo_dp_bound(float epsilon, int tau);

@@ -111,6 +111,8 @@ def oracle():
                                         C.POINTER(C.c_uint32)]
         L.mfo_philox_normal4.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int32, C.c_int64,
                                          C.c_uint32, f32p]
+        L.mfo_philox_bias_normal.restype = C.c_float
+        L.mfo_philox_bias_normal.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int32, C.c_int64]
         _oracle = L
     return _oracle
 

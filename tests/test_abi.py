@@ -93,6 +93,56 @@ def test_wire_kat_and_errors(tmp_path):
         mb.Blocks.read(str(tmp_path / "nope.bin"))
 
 
+def _varint(v):
+    out = bytearray()
+    v &= (1 << 64) - 1
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_wire_decoder_fast_path_and_general_path_agree(tmp_path):
+    """The decoder has a fast path for the canonical record (12 LL 08 <vid> 15 <f32>) and a general
+    one; any legal encoding of the same messages (field order swapped, unknown fields, over-long
+    varints, item ids of every varint width) must decode to the same arrays."""
+    import struct
+    vids = [0, 1, 127, 128, 300, 16383, 16384, 65535, 2097151, 2097152, 268435455, 2**31 - 1]
+    ratings = [float(i % 5 + 1) for i in range(len(vids))]
+
+    def user(uid, recs):
+        body = b"\x08" + _varint(uid) + b"".join(recs)
+        return b"\x0a" + _varint(len(body)) + body
+
+    canon = [b"\x12" + _varint(len(_varint(v)) + 6) + b"\x08" + _varint(v) + b"\x15" + struct.pack("<f", r)
+             for v, r in zip(vids, ratings)]
+    odd = []
+    for i, (v, r) in enumerate(zip(vids, ratings)):
+        f1, f2 = b"\x08" + _varint(v), b"\x15" + struct.pack("<f", r)
+        if i % 3 == 0:
+            body = f2 + f1                                  # rating before vid
+        elif i % 3 == 1:
+            body = f1 + b"\x18\x07" + f2                    # unknown varint field 3
+        else:
+            body = b"\x08" + _varint(v)[:-1] + bytes([_varint(v)[-1] | 0x80, 0x00]) + f2  # over-long varint
+        odd.append(b"\x12" + _varint(len(body)) + body)
+    for name, recs in (("canon", canon), ("odd", odd)):
+        blk = user(7, recs) + user(9, []) + user(300, recs[:3])
+        path = tmp_path / (name + ".bin")
+        path.write_bytes(struct.pack("<I", len(blk)) + blk)
+        b = mb.Blocks.read(str(path))
+        assert b.run_uid.tolist() == [7, 9, 300]
+        assert b.run_off.tolist() == [0, len(vids), len(vids), len(vids) + 3]
+        assert b.vid.tolist() == vids + vids[:3]
+        assert b.rating.tolist() == ratings + ratings[:3]
+    # a record cut short inside the fast path's window is an error, not a read past the frame
+    blk = user(7, canon)[:-2]
+    (tmp_path / "short.bin").write_bytes(struct.pack("<I", len(blk)) + blk)
+    with pytest.raises(mb.MfbError):
+        mb.Blocks.read(str(tmp_path / "short.bin"))
+
+
 def test_wire_roundtrip_agrees_with_oracle_codec(oracle_lib, tmp_path):
     train, test, _ = ol.make_ratings(200, 90, 5000, seed=12)
     p = train.write(str(tmp_path / "o.bin"))  # written by the oracle's encoder

@@ -108,6 +108,27 @@ def test_philox_normals_moments(oracle_lib):
     assert abs((x ** 3).mean()) < 0.06 and abs((x ** 4).mean() - 3) < 0.15
 
 
+def test_philox_bias_normal_moments_and_independence(oracle_lib):
+    """The bias normal of (kind,row,t) is built from the low bytes of chunks 0 and 1 - bits the
+    factor normals (top 24 bits of each word) do not use: N(0,1) moments, and no correlation with
+    the factor normals of the same two chunks."""
+    z0, z1 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    b, f = [], []
+    for t in range(20000):
+        args = (0x4D46B200, 2, t & 1, t % 89, t)
+        b.append(oracle_lib.mfo_philox_bias_normal(*args))
+        oracle_lib.mfo_philox_normal4(*args, 0, _p(z0, f32p))
+        oracle_lib.mfo_philox_normal4(*args, 1, _p(z1, f32p))
+        f.append(np.concatenate([z0, z1]))
+    b, f = np.array(b, np.float64), np.array(f, np.float64)
+    assert abs(b.mean()) < 0.03 and abs(b.var() - 1) < 0.04
+    assert abs((b ** 3).mean()) < 0.1 and abs((b ** 4).mean() - 3) < 0.25
+    corr = [abs(np.corrcoef(b, f[:, i])[0, 1]) for i in range(8)]
+    assert max(corr) < 0.03, corr
+    corr2 = [abs(np.corrcoef(b ** 2, f[:, i] ** 2)[0, 1]) for i in range(8)]
+    assert max(corr2) < 0.03, corr2
+
+
 def test_seteta_formula(oracle_lib):
     # model.cc:36-38 eta = eta0 / round^gam in double, narrowed
     for eta0, rnd, gam in ((2e-2, 1, 1.0), (2e-2, 7, 1.0), (4e-2, 3, 0.6)):
