@@ -36,6 +36,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// The ten round keys of one seed, computed once on the host and passed with the kernel arguments: the
+// kernel then reads them as constant-bank operands of the XORs instead of re-deriving them (18
+// uniform-datapath additions per record in the dpmf kernel, each an issue slot).
+static inline void philox_round_keys(uint64_t seed, uint32_t rk[20]) {
+  uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    rk[2 * r] = kx;
+    rk[2 * r + 1] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0, lo0, hi1, lo1;
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p; }" : "=r"(lo0), "=r"(hi0) : "r"(c.x), "r"(0xD2511F53u));
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p; }" : "=r"(lo1), "=r"(hi1) : "r"(c.z), "r"(0xCD9E8D57u));
+    c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+
 // the 24 bits of a Philox block that box_muller4 does not use: low bytes of words x, y, z
 __device__ __forceinline__ uint32_t spare_bits24(uint4 x) {
   return (x.x & 0xFFu) | ((x.y & 0xFFu) << 8) | ((x.z & 0xFFu) << 16);
@@ -68,17 +91,20 @@ __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.
 __device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// r^2 = -2 ln(m 2^-24) = -2 ln2 (lg2 m - 24): the scaling of u1 folds into one FFMA after the MUFU;
+// the angle takes the whole 32-bit word (rounded to 24 bits by the conversion, at most half a unit
+// of the truncated value the exact transform uses).
 __device__ __forceinline__ float4 box_muller4_fast(uint4 x) {
-  const float s = 1.0f / 16777216.0f, w = 6.28318530717958647692f / 16777216.0f;
-  const float u1 = ((float)(x.x >> 8) + 1.0f) * s, a0 = (float)(x.y >> 8) * w;
-  const float u3 = ((float)(x.z >> 8) + 1.0f) * s, a1 = (float)(x.w >> 8) * w;
-  const float r0 = mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u1));
-  const float r1 = mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u3));
+  const float c2 = -1.38629436111989061883f, c0 = 24.0f * 1.38629436111989061883f;
+  const float w = 6.28318530717958647692f / 4294967296.0f;
+  const float r0 = mufu_sqrt(fmaf(mufu_lg2((float)((x.x >> 8) + 1u)), c2, c0));
+  const float r1 = mufu_sqrt(fmaf(mufu_lg2((float)((x.z >> 8) + 1u)), c2, c0));
+  const float a0 = (float)x.y * w, a1 = (float)x.w * w;
   return make_float4(r0 * mufu_cos(a0), r0 * mufu_sin(a0), r1 * mufu_cos(a1), r1 * mufu_sin(a1));
 }
 __device__ __forceinline__ float box_muller_bias_fast(uint32_t s0, uint32_t s1) {
-  const float u1 = ((float)s0 + 1.0f) * (1.0f / 16777216.0f);
-  return mufu_sqrt(-1.38629436111989061883f * mufu_lg2(u1)) * mufu_cos((float)s1 * (6.28318530717958647692f / 16777216.0f));
+  const float c2 = -1.38629436111989061883f, c0 = 24.0f * 1.38629436111989061883f;
+  return mufu_sqrt(fmaf(mufu_lg2((float)(s0 + 1u)), c2, c0)) * mufu_cos((float)s1 * (6.28318530717958647692f / 16777216.0f));
 }
 
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t round, int kind,

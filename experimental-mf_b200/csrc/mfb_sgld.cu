@@ -43,6 +43,7 @@ struct SgldArgs {
   float eta, temp, bound, scal, lambda_ub, lambda_vb, gb;
   uint64_t seed;
   uint32_t round;
+  uint32_t rk[20];     // Philox round keys of `seed` (philox_round_keys)
   const float* table;  // ordered parity mode only: the reference's noise_ table
   int table_offset;
 };
@@ -55,16 +56,18 @@ __device__ __forceinline__ Row<VPL> noise_chunks(const SgldArgs& a, int kind, in
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
     const int v = gl + i * LPR;
-    const uint4 x = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)row, (uint32_t)v, (uint32_t)kind + 2u * a.round),
-                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    const uint4 x = philox4x32_10_rk(make_uint4((uint32_t)t, (uint32_t)row, (uint32_t)v, (uint32_t)kind + 2u * a.round), a.rk);
     if (i == 0) *spare = spare_bits24(x);
     z.v[i] = FAST ? box_muller4_fast(x) : box_muller4(x);
-    // coordinates >= dim are padding: keep them exactly zero
-    const int c = 4 * v;
-    if (c + 0 >= a.dim) z.v[i].x = 0.f;
-    if (c + 1 >= a.dim) z.v[i].y = 0.f;
-    if (c + 2 >= a.dim) z.v[i].z = 0.f;
-    if (c + 3 >= a.dim) z.v[i].w = 0.f;
+    // coordinates >= dim are padding: keep them exactly zero (a uniform branch: rows that fill
+    // the group's lanes exactly, e.g. k = 128, skip the eight selects)
+    if (a.dim < 4 * LPR * VPL) {
+      const int c = 4 * v;
+      if (c + 0 >= a.dim) z.v[i].x = 0.f;
+      if (c + 1 >= a.dim) z.v[i].y = 0.f;
+      if (c + 2 >= a.dim) z.v[i].z = 0.f;
+      if (c + 3 >= a.dim) z.v[i].w = 0.f;
+    }
   }
   return z;
 }
@@ -98,11 +101,10 @@ __device__ __forceinline__ void noise_pair(const SgldArgs& a, int uid, int v, in
   xu = noise_chunks<LPR, VPL, FAST>(a, 0, uid, t, gl, &su);
   xv = noise_chunks<LPR, VPL, FAST>(a, 1, v, t, gl, &sv);
   const uint32_t other = __shfl_xor_sync(m, gl == 0 ? sv : su, 1, LPR);
-  float b = 0.f;
-  if (gl < 2) {
-    const uint32_t s0 = gl == 0 ? su : other, s1 = gl == 0 ? other : sv;
-    b = FAST ? box_muller_bias_fast(s0, s1) : box_muller_bias(s0, s1);
-  }
+  // (every lane evaluates the transform - the same warp instructions as a guarded one, without the
+  // divergence bookkeeping; only lanes 0 and 1 hold meaningful bits)
+  const uint32_t s0 = gl == 0 ? su : other, s1 = gl == 0 ? other : sv;
+  const float b = FAST ? box_muller_bias_fast(s0, s1) : box_muller_bias(s0, s1);
   *xbu = __shfl_sync(m, b, 0, LPR);
   *xbv = __shfl_sync(m, b, 1, LPR);
 }
@@ -323,6 +325,7 @@ struct FlushArgs {
   float eta, temp;
   uint64_t seed;
   uint32_t round;
+  uint32_t rk[20];
   const float* table;
   int table_offset;
 };
@@ -336,6 +339,8 @@ __global__ void __launch_bounds__(256) sgld_flush_kernel(const FlushArgs f) {
   a.dim = f.dim;
   a.seed = f.seed;
   a.round = f.round;
+#pragma unroll
+  for (int i = 0; i < 20; i++) a.rk[i] = f.rk[i];
   a.table = f.table;
   a.table_offset = f.table_offset;
   for (int row = g; row < f.rows; row += G) {
@@ -452,6 +457,7 @@ int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int 
   a.gb = gb;
   a.seed = p->seed;
   a.round = p->round;
+  philox_round_keys(p->seed, a.rk);
   a.table = p->use_table ? c->d_noise_table : nullptr;
   a.table_offset = p->table_offset;
   MFB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
@@ -476,6 +482,7 @@ int launch_flush(Context* c, Dataset* d, const mfb_sgld_params* p) {
     f.temp = p->temp;
     f.seed = p->seed;
     f.round = p->round;
+    philox_round_keys(p->seed, f.rk);
     f.table = p->use_table ? c->d_noise_table : nullptr;
     f.table_offset = p->table_offset;
 #define CALL(L, V) { int rc = launch_flush_t<L, V>(c, f); if (rc) return rc; }
