@@ -44,6 +44,7 @@ struct AdmfArgs {
   float* lams;           // [4] lam_u, lam_v, lam_bu, lam_bv (16-byte aligned)
   int* counter;
   int nruns, nvec, loss;
+  int prefetch;          // parallel schedule: request the item row of record j+1 before working on record j
   float eta, eta_reg, gb;
 };
 
@@ -129,12 +130,12 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
           myvid = q < hi ? __ldcs(a.vid + q) : 0;
           myr = q < hi ? __ldcs(a.rating + q) : 0.f;
         }
-        if (ORDERED || b == 0) fetch(b);  // the ordered schedule reads every row after the previous update
+        if (ORDERED || !a.prefetch || b == 0) fetch(b);  // the ordered schedule reads every row after the previous update
         const int v = v_n;
         const float r = __shfl_sync(m, myr, b, LPR);
         Row<VPL> f = f_n;
         float bvv = __shfl_sync(m, bv_n, 0, LPR);
-        if (!ORDERED && b + 1 < LPR && j + 1 < hi) fetch(b + 1);
+        if (!ORDERED && a.prefetch && b + 1 < LPR && j + 1 < hi) fetch(b + 1);
         t_prev = t;                                                    // admf.h:67
         bu_prev = bu;                                                  // admf.h:77
         store_row_f<LPR, VPL>(a.phi_old, v, a.nvec, gl, f, ORDERED ? 0 : 1);  // admf.h:68
@@ -253,8 +254,13 @@ int launch_admf_t(Context* c, const Dataset* d, const AdmfArgs& a, int mode) {
   } else {
     auto k = admf_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC>;
     // The regularisers are learned from the same stale rows, which makes this path less tolerant than
-    // plain SGD (measured: NaN at 6 times this width at eta = 0.02); the step of a stale update is eta.
-    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, 6, a.eta);
+    // plain SGD; the step of a stale update is eta.  A run holds two item rows between gather and
+    // reduction (the current one and the one requested ahead); it counts for 3 in the hot-row budget
+    // (option admf_weight).  Measured at the Netflix shape, k = 64 (tools/exp_admf_width.py): weight
+    // 6 -> 3 halves the first epochs (102.7/54.0/37.8/29.7 -> 54.0/29.7/21.6/21.6 ms) and moves the
+    // test RMSE by <= 4e-4 and lam_bu by 0.5 %; weight 2: <= 6e-4 and 1.3 %; weight 1 without the
+    // row request ahead: 1.4e-3 and 3 %.  3,552 warps (registers) is the hardware limit.
+    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, c->opt_admf_weight, a.eta);
     k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
   }
   MFB_CUDA(cudaGetLastError());
@@ -287,6 +293,7 @@ int launch_admf(Context* c, Dataset* d, float eta, float eta_reg, int loss, floa
   a.nruns = (int)d->nruns;
   a.nvec = c->stride / 4;
   a.loss = loss;
+  a.prefetch = c->opt_admf_prefetch;
   a.eta = eta;
   a.eta_reg = eta_reg;
   a.gb = gb;

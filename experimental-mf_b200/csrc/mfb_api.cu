@@ -314,6 +314,11 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "eta_scaling")) {
     MFB_REQUIRE(value >= 0 && value <= 2, "eta_scaling must be 0, 1 (row budget) or 2 (row and run budgets)");
     c->opt_eta_scaling = value;
+  } else if (!strcmp(name, "admf_weight")) {
+    MFB_REQUIRE(value >= 1 && value <= 64, "admf_weight must be 1..64");
+    c->opt_admf_weight = value;
+  } else if (!strcmp(name, "admf_prefetch")) {
+    c->opt_admf_prefetch = value != 0;
   } else if (!strcmp(name, "memopt")) {
     c->opt_memopt = value;
   } else {

@@ -134,6 +134,8 @@ struct Context {
   int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)
   int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
   int last_grid = 0, last_threads = 0, last_ring = 0;  // launch shape of the most recent epoch kernel
+  int opt_admf_weight = 3;      // admf kernel: item rows a run counts for in the hot-row budget
+  int opt_admf_prefetch = 1;    // admf kernel: next item row requested one record ahead
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
   std::vector<Dataset> datasets;
