@@ -124,6 +124,113 @@ static void free_ds_device(Dataset* d) {
   d->d_uc = d->d_vc = d->d_last_u = d->d_last_v = nullptr;
 }
 
+int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) {
+  if (c->placement_done) return MFB_OK;
+  const int trials = std::min(c->opt_placement_trials, 64);
+  if (trials <= 1 || (mode != MFB_MODE_ATOMIC && mode != MFB_MODE_HOGWILD)) return MFB_OK;
+  int64_t total = 0;
+  for (int i = 0; i < nds; i++) total += ds[i]->nratings;
+  if (total < c->placement_min_ratings) return MFB_OK;  // (not marked done: a larger file may follow)
+  c->placement_done = true;
+  const size_t phi_bytes = ((size_t)c->nv * c->stride + 15) / 16 * 16 * sizeof(float);
+  const size_t bv_bytes = ((size_t)c->nv + 15) / 16 * 16 * sizeof(float);
+  const size_t slot = (phi_bytes + bv_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  float* const phi0 = c->arr[MFB_PHI];
+  float* const bv0 = c->arr[MFB_BV];
+  // candidate 0 is where the arrays are; the others are slots of ONE arena that stays allocated (a few
+  // hundred MB at most; freeing per candidate would cost more time than the calibration itself)
+  int n = trials;
+  char* arena = nullptr;
+  while (n > 1 && cudaMalloc(&arena, (size_t)(n - 1) * slot) != cudaSuccess) {
+    cudaGetLastError();
+    arena = nullptr;
+    n = (n + 1) / 2;
+  }
+  if (!arena) return MFB_OK;
+  auto phi_of = [&](int i) { return i == 0 ? phi0 : (float*)(arena + (size_t)(i - 1) * slot); };
+  auto bv_of = [&](int i) { return i == 0 ? bv0 : (float*)(arena + (size_t)(i - 1) * slot + phi_bytes); };
+  cudaEvent_t e0, e1;
+  MFB_CUDA(cudaEventCreate(&e0));
+  MFB_CUDA(cudaEventCreate(&e1));
+  // the launch of the steady state: as wide as the run bound allows, deepest ring; probe off
+  const int save_kernel = c->opt_kernel, save_ring = c->opt_ring, save_groups = c->opt_max_groups;
+  const bool save_timed = c->timed;
+  int* const save_version = c->d_version;
+  c->d_version = nullptr;
+  int rc = MFB_OK;
+  auto calibrate = [&](int divisor) {
+    for (int i = 0; i < nds && rc == MFB_OK; i++) {
+      Dataset* d = ds[i];
+      if (!d->nruns) continue;
+      c->opt_kernel = 0;
+      c->opt_ring = 0;
+      c->opt_max_groups = (int)std::max<int64_t>(1, bounded_groups_alone(c, (int64_t)c->sm_count * 64, d->max_item_share,
+                                                                         d->nruns, 4.0, 0.02f / 8));
+      const int64_t prefix = std::min<int64_t>(d->nruns, std::max<int64_t>(d->nruns / divisor, 100000));
+      rc = launch_sgd(c, d, 0.f, 0.f, gb, mode, 0, prefix);
+    }
+  };
+  auto timed_run = [&](int i, int divisor, float* ms) -> int {
+    c->arr[MFB_PHI] = phi_of(i);
+    c->arr[MFB_BV] = bv_of(i);
+    MFB_CUDA(cudaEventRecord(e0, c->stream));
+    calibrate(divisor);
+    MFB_CUDA(cudaEventRecord(e1, c->stream));
+    MFB_CUDA(cudaEventSynchronize(e1));
+    MFB_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    return rc;
+  };
+  calibrate(10);  // warm-up, not timed
+  for (int i = 1; i < n && rc == MFB_OK; i++) {
+    if (cudaMemcpyAsync(phi_of(i), phi0, phi_bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(bv_of(i), bv0, bv_bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
+      set_error("placement search: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = MFB_E_CUDA;
+    }
+  }
+  // stage 1: every candidate over the first tenth of the file(s); stage 2: the three fastest over the
+  // first two fifths (a short prefix sees the launch tail and a narrower mix of items)
+  std::vector<std::pair<float, int>> order;
+  for (int i = 0; i < n && rc == MFB_OK; i++) {
+    float ms = 0.f;
+    rc = timed_run(i, 10, &ms);
+    c->placement_ms[i] = ms;
+    order.push_back({ms, i});
+  }
+  int best = 0;
+  if (rc == MFB_OK) {
+    std::sort(order.begin(), order.end());
+    float best_ms = 0.f;
+    for (size_t j = 0; j < order.size() && j < 3 && rc == MFB_OK; j++) {
+      float ms = 0.f;
+      rc = timed_run(order[j].second, 5, &ms);
+      rc = rc ? rc : timed_run(order[j].second, 5, &ms);
+      if (j == 0 || ms < best_ms) { best = order[j].second; best_ms = ms; }
+    }
+    c->placement_tried = n;
+    c->placement_best = best;
+  }
+  c->opt_kernel = save_kernel;
+  c->opt_ring = save_ring;
+  c->opt_max_groups = save_groups;
+  c->timed = save_timed;
+  c->d_version = save_version;
+  cudaStreamSynchronize(c->stream);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // every candidate holds the same (unchanged) values: keep the fastest
+  c->arr[MFB_PHI] = phi_of(best);
+  c->arr[MFB_BV] = bv_of(best);
+  if (best == 0) {
+    cudaFree(arena);
+  } else {
+    c->placement_arena = arena;
+    cudaFree(phi0);
+    cudaFree(bv0);
+  }
+  return rc;
+}
+
 static void begin_timing(Context* c) {
   cudaEventRecord(c->ev0, c->stream);
 }
@@ -224,6 +331,10 @@ void mfb_destroy(mfb_ctx* h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& d : c->datasets) free_ds_device(&d);
+  if (c->placement_arena) {  // phi/bv live inside the arena of the placement search
+    c->arr[MFB_PHI] = c->arr[MFB_BV] = nullptr;
+    cudaFree(c->placement_arena);
+  }
   for (auto& p : c->arr) cudaFree(p);
   cudaFree(c->d_counter);
   cudaFree(c->d_accum);
@@ -314,6 +425,12 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "eta_scaling")) {
     MFB_REQUIRE(value >= 0 && value <= 2, "eta_scaling must be 0, 1 (row budget) or 2 (row and run budgets)");
     c->opt_eta_scaling = value;
+  } else if (!strcmp(name, "placement_trials")) {
+    MFB_REQUIRE(value >= 0 && value <= 64, "placement_trials must be 0..64");
+    c->opt_placement_trials = value;
+  } else if (!strcmp(name, "placement_min_ratings")) {
+    MFB_REQUIRE(value >= 0, "placement_min_ratings must be >= 0");
+    c->placement_min_ratings = value;
   } else if (!strcmp(name, "admf_weight")) {
     MFB_REQUIRE(value >= 1 && value <= 64, "admf_weight must be 1..64");
     c->opt_admf_weight = value;
@@ -557,6 +674,7 @@ int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mod
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC,
               "bad mode %d", mode);
   MFB_CUDA(cudaSetDevice(c->device));
+  if (int trc = tune_placement(c, &d, 1, gb, mode)) return trc;
   begin_timing(c);
   int rc = MFB_OK;
   const int64_t parts = std::max(1, c->opt_epoch_launches);  // diagnostic: the epoch as several launches
@@ -585,6 +703,9 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC, "streamed epochs are Hogwild/atomic only");
   MFB_CUDA(cudaSetDevice(c->device));
   if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!d->refresh_pending) {  // (the tiles are resident from finalize: the calibration can use them)
+    if (int trc = tune_placement(c, &d, 1, gb, mode)) return trc;
+  }
   if (chunk_ratings <= 0) chunk_ratings = 3 << 20;
   // Chunks grow geometrically by 7/4 up to 6x the given size: the first kernel starts after a small
   // copy and every later copy is shorter than the kernels it hides behind (measured while kernels
@@ -1060,6 +1181,14 @@ float mfb_last_kernel_ms(mfb_ctx* h) {
 
 int64_t mfb_launch_count(mfb_ctx* h) { return h ? h->c.launches : 0; }
 int64_t mfb_h2d_bytes(mfb_ctx* h) { return h ? h->c.h2d_bytes : 0; }
+
+int mfb_placement_report(mfb_ctx* h, float* ms, int n, int* best) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  const Context* c = &h->c;
+  for (int i = 0; i < c->placement_tried && i < n; i++) ms[i] = c->placement_ms[i];
+  if (best) *best = c->placement_best;
+  return std::min(n, c->placement_tried);
+}
 
 int mfb_last_launch(mfb_ctx* h, int out[4]) {
   MFB_REQUIRE(h && out, "NULL argument");

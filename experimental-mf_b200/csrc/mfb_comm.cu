@@ -12,6 +12,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "mfb_internal.h"
 
@@ -71,6 +72,10 @@ struct Comm {
   cudaStream_t stream = nullptr;
   cudaEvent_t computed = nullptr, shifted = nullptr;
   double* d_red = nullptr;  // [2] sse, count
+  // diagnostic timeline of the most recent epoch (mfb_dsgd_timeline): events on the compute stream
+  // at the start of the epoch, after every cell kernel and after every wait for the ring shift
+  std::vector<cudaEvent_t> marks;
+  int nmarks = 0;
 };
 
 }  // namespace mfb
@@ -116,6 +121,7 @@ int mfb_comm_destroy(mfb_ctx* h) {
   cudaStreamSynchronize(m->stream);
   cudaStreamSynchronize(c->stream);
   if (m->nccl) g_nccl.CommDestroy(m->nccl);
+  for (cudaEvent_t e : m->marks) cudaEventDestroy(e);
   cudaEventDestroy(m->computed);
   cudaEventDestroy(m->shifted);
   cudaStreamDestroy(m->stream);
@@ -154,7 +160,25 @@ int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, 
   const int P = m->world;
   MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[P] == c->nv, "item_bounds must span [0, nv]");
   MFB_CUDA(cudaSetDevice(c->device));
+  if (!c->placement_done) {  // placement of this rank's copy of the item matrix, over all of its cells
+    std::vector<Dataset*> cells;
+    for (int b = 0; b < P; b++) {
+      const int ds = datasets[b];
+      MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].finalized, "bad dataset for block %d", b);
+      if (!c->datasets[ds].refresh_pending) cells.push_back(&c->datasets[ds]);
+    }
+    if ((int)cells.size() == P) {
+      if (int trc = tune_placement(c, cells.data(), P, gb, mode)) return trc;
+    }
+  }
   cudaEventRecord(c->ev0, c->stream);
+  if ((int)m->marks.size() < 2 * P + 1) {
+    const size_t old = m->marks.size();
+    m->marks.resize(2 * P + 1);
+    for (size_t i = old; i < m->marks.size(); i++) MFB_CUDA(cudaEventCreate(&m->marks[i]));
+  }
+  m->nmarks = 0;
+  MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
   for (int s = 0; s < P; s++) {
     const int b = (m->rank + s) % P, nb = (b + 1) % P;
     const int ds = datasets[b];
@@ -164,14 +188,30 @@ int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, 
       int rc = launch_sgd(c, d, eta, lambda, gb, mode, 0, d->nruns);
       if (rc) return rc;
     }
+    MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
     if (P > 1) {
       int rc = shift_block(c, m, item_bounds, b, nb);
       if (rc) return rc;
     }
+    MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
   }
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;
   return MFB_OK;
+}
+
+// Diagnostic: where the most recent mfb_dsgd_epoch spent its time on this rank.  out[2s] = ms of the
+// cell kernel of sub-epoch s, out[2s+1] = ms the compute stream then waited for the ring shift (send of
+// the block just updated + arrival of the next one, i.e. also the neighbour's cell still running).
+int mfb_dsgd_timeline(mfb_ctx* h, float* out, int n) {
+  MFB_REQUIRE(h && out, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m && m->nmarks > 1, "no epoch recorded");
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaEventSynchronize(m->marks[m->nmarks - 1]));
+  for (int i = 0; i + 1 < m->nmarks && i < n; i++) MFB_CUDA(cudaEventElapsedTime(out + i, m->marks[i], m->marks[i + 1]));
+  return std::min(n, m->nmarks - 1);
 }
 
 // every rank publishes its home block (block == rank): afterwards all ranks hold all of phi/bv

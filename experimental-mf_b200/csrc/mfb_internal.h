@@ -134,6 +134,13 @@ struct Context {
   int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)
   int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
   int last_grid = 0, last_threads = 0, last_ring = 0;  // launch shape of the most recent epoch kernel
+  int opt_placement_trials = 16; // candidate placements of the item matrix tried before the first parallel epoch
+                                // on a file of >= placement_min_ratings records (<= 1: off); tune_placement()
+  int64_t placement_min_ratings = 4000000;
+  bool placement_done = false;
+  float placement_ms[64] = {0};  // diagnostic: calibration time of every candidate (mfb_placement_report)
+  int placement_tried = 0, placement_best = -1;
+  char* placement_arena = nullptr;  // holds phi/bv when a candidate other than the original allocation won
   int opt_admf_weight = 3;      // admf kernel: item rows a run counts for in the hot-row budget
   int opt_admf_prefetch = 1;    // admf kernel: next item row requested one record ahead
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
@@ -164,6 +171,14 @@ int64_t bounded_groups(const Context* c, int64_t groups, double max_item_share, 
 LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_needed,
                         double max_item_share, int64_t total_runs, int inflight = 6, float eta = 0.f);
 
+// Where the item matrix lives decides the epoch time: the L2 slice of a line is a hash of its PHYSICAL
+// address, the hottest slice bounds the atomic throughput, and which slices the rows of the most rated
+// items share is luck per allocation (measured on one GPU, same data: 15.2 .. 19.6 ms per epoch over 8
+// allocations, tools/exp_placement.py).  tune_placement copies phi/bv to `placement_trials` candidate
+// allocations, runs the parallel SGD kernel with eta = 0 (increments of exactly zero: the model is
+// unchanged, the memory traffic is the real one) over the first fifth of every given dataset on each,
+// and keeps the fastest.  Once per context.
+int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode);
 // kernels (mfb_sgd.cu)
 // runs [run_begin, run_end) of the dataset, in the given schedule
 int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mode,

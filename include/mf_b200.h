@@ -240,6 +240,10 @@ int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
 int mfb_comm_destroy(mfb_ctx* ctx);
 int mfb_dsgd_epoch(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
                    float gb, int mode);
+/* diagnostic: the most recent mfb_dsgd_epoch on this rank as out[2s] = ms of the cell kernel of sub-epoch
+ * s, out[2s+1] = ms the compute stream then waited for the ring shift; returns the number of entries
+ * written (<= n) or a negative error */
+int mfb_dsgd_timeline(mfb_ctx* ctx, float* out, int n);
 /* make all of phi/bv valid on every rank (each rank publishes its home block) - before evaluation */
 int mfb_comm_allgather_items(mfb_ctx* ctx, const int32_t* item_bounds);
 /* sum (sse, n) over the ranks */
@@ -259,6 +263,12 @@ float mfb_last_kernel_ms(mfb_ctx* ctx);
 int64_t mfb_launch_count(mfb_ctx* ctx);
 /* bytes copied host -> device by mfb_sgd_epoch_from_host since the context was created */
 int64_t mfb_h2d_bytes(mfb_ctx* ctx);
+/* Placement search of the item matrix: before the first parallel SGD epoch on a file of
+ * at least "placement_min_ratings" records (option, default 4,000,000) the library tries
+ * "placement_trials" (option, default 16; <= 1 turns it off) allocations for phi/bv and keeps the fastest
+ * - mfb_device_ptr(MFB_PHI / MFB_BV) may therefore change once, at that first epoch.  The report: ms[i] =
+ * calibration time of candidate i, *best = the one kept; returns the number of candidates tried. */
+int mfb_placement_report(mfb_ctx* ctx, float* ms, int n, int* best);
 /* shape of the most recent SGD epoch launch: out = {kernel variant, grid, threads per CTA, ring depth} */
 int mfb_last_launch(mfb_ctx* ctx, int out[4]);
 
