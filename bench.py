@@ -304,12 +304,14 @@ def run_b200_arm(args, wl):
     sampler = ClockSampler(local)
     sampler.start()
     kern_ms = []
+    launches_a = c.launch_count()
     ev[0].record(stream)
     for _ in range(args.steps):
         step_resident()
         kern_ms.append(None)
     ev[1].record(stream)
     torch.cuda.synchronize()
+    launches_resident = c.launch_count() - launches_a
     total_ms = ev[0].elapsed_time(ev[1])
     # the kernel's own duration, launch by launch (events recorded by the library around the
     # kernel on the same stream): a second, identical timed pass keeps the first one unperturbed
@@ -339,6 +341,7 @@ def run_b200_arm(args, wl):
         step_e2e()
     torch.cuda.synchronize()
     h2d0 = c.h2d_bytes()
+    launches_b = c.launch_count()
     t0 = time.perf_counter()
     ev[0].record(stream)
     for _ in range(args.steps):
@@ -350,7 +353,8 @@ def run_b200_arm(args, wl):
     h2d = (c.h2d_bytes() - h2d0) // args.steps
     e2e_ms = max(ev[0].elapsed_time(ev[1]), 1e3 * e2e_wall)
     e2e_value = ntrain * args.steps / (e2e_ms * 1e-3)
-    launches = c.launch_count() - launches0
+    launches_e2e = c.launch_count() - launches_b
+    launches = launches_resident + launches_e2e  # kernels launched inside the two timed regions
     final_rmse = float(np.sqrt(sse_host[-1] / te.nratings))
     tr.unpin()
 
@@ -382,6 +386,9 @@ def run_b200_arm(args, wl):
                 "what": "mfb_sgd_epoch_from_host (pinned host tiles, compact 3-byte records when the data allow -> "
                         "chunked H2D overlapped with the kernel, expanded on the device) + mfb_sse"},
         "clocks": clocks, "gpu_launches": launches,
+        "gpu_launches_detail": {"resident_leg": launches_resident, "e2e_leg": launches_e2e,
+                                "whole_run": c.launch_count() - launches0},
+        "placement": dict(zip(("calibration_ms", "kept"), c.placement_report())),
         "test_rmse": final_rmse, "test_rmse_after_resident_leg": rmse_resident,
         "epochs_run": epoch[0], "train_ratings": ntrain, "gen_s": round(gen_s, 2), "ingest_s": round(ingest_s, 2),
     }

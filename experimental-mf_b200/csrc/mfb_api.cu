@@ -167,7 +167,7 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) 
       c->opt_max_groups = (int)std::max<int64_t>(1, bounded_groups_alone(c, (int64_t)c->sm_count * 64, d->max_item_share,
                                                                          d->nruns, 4.0, 0.02f / 8));
       const int64_t prefix = std::min<int64_t>(d->nruns, std::max<int64_t>(d->nruns / divisor, 100000));
-      rc = launch_sgd(c, d, 0.f, 0.f, gb, mode, 0, prefix);
+      rc = launch_sgd(c, d, 0.f, 0.f, gb, MFB_MODE_ATOMIC, 0, prefix);  // increments of exactly zero
     }
   };
   auto timed_run = [&](int i, int divisor, float* ms) -> int {

@@ -118,7 +118,9 @@ def bench(args, wl, shape, rank, world, local, config):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    la = w.ctx.launch_count()
     total_ms, _ = timed(step, args.steps)
+    launches_resident = w.ctx.launch_count() - la
     tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
     dist.all_reduce(tot)
     ntrain = int(tot[0])
@@ -137,14 +139,16 @@ def bench(args, wl, shape, rank, world, local, config):
         sse_host.append(w.global_sse(GB))
 
     step_e2e()
+    lb = w.ctx.launch_count()
     e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps)
+    launches_e2e = w.ctx.launch_count() - lb
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed legs
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)
     h2d = sum(b.nratings * 8 + b.nruns * 8 + 4 for b in w.cells)
     h2d_t = torch.tensor([h2d], dtype=torch.int64, device="cuda")
     dist.all_reduce(h2d_t)
     sse, n = sse_host[-1]
-    launches = w.ctx.launch_count() - launches0
+    launches = launches_resident + launches_e2e  # this rank's kernels inside the two timed regions
     shape = w.ctx.last_launch()
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -161,7 +165,11 @@ def bench(args, wl, shape, rank, world, local, config):
                     "h2d_bytes_per_step": int(h2d_t[0]), "d2h_bytes_per_step": 16 * world,
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "per rank: H2D of its cell tiles + mfb_dsgd_epoch + gathered test SSE, max over ranks"},
-            "clocks": clocks, "gpu_launches": launches, "test_rmse": float(np.sqrt(sse / max(n, 1))),
+            "clocks": clocks, "gpu_launches": launches,
+            "gpu_launches_detail": {"per": "rank 0", "resident_leg": launches_resident, "e2e_leg": launches_e2e,
+                                    "whole_run": w.ctx.launch_count() - launches0},
+            "placement": dict(zip(("calibration_ms", "kept"), w.ctx.placement_report())),
+            "test_rmse": float(np.sqrt(sse / max(n, 1))),
             "epochs_run": epoch[0], "train_ratings": ntrain, "gen_s": round(gen_s, 2),
             "dsgd": {"cells_per_rank": world, "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
                      "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch"},
