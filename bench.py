@@ -51,7 +51,7 @@ KERNEL_NAMES = {1: "sgd_epoch_kernel (warp per run)", 2: "sgd_epoch_kernel_b4 (w
 def profiled_traffic(schedule):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the update kernel, from the
     committed ncu --set full capture of this same command (profiles/, made by tools/ncu_summary.py)."""
-    p = os.path.join(ROOT, "profiles", "r1_sgd_stream.json" if schedule == "atomic" else "r1_sgd_%s.json" % schedule)
+    p = os.path.join(ROOT, "profiles", "r1_sgd_stream_placed.json" if schedule == "atomic" else "r1_sgd_%s.json" % schedule)
     try:
         return float(json.load(open(p))["launches"][0]["dram_traffic_bytes"]), os.path.relpath(p, ROOT)
     except (OSError, KeyError, IndexError, ValueError):
@@ -379,7 +379,8 @@ def run_b200_arm(args, wl):
                      "note": "algorithmic bytes (rating record + two factor rows read and written per update); "
                              "theta rows stay in registers across a user-run and the item matrix (9.1 MB) lives in "
                              "L2, so DRAM traffic is far lower and the fraction exceeds 1; the physical bound is "
-                             "the L2 atomic unit of the hottest slice (profiles/r1_sgd_stream.md)"},
+                             "the L2 atomic unit of the hottest slice (profiles/r1_sgd_stream_placed.md), which is why the "
+                             "library searches the placement of the item matrix before the first epoch"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / args.steps,

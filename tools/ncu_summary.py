@@ -14,7 +14,21 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
         "smsp__average_warp_latency_per_inst_issued.ratio", "launch__registers_per_thread",
-        "launch__grid_size", "launch__block_size", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "launch__grid_size", "launch__block_size", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        # per-slice balance of the L2 (avg / max / min over the slices)
+        "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__d_atomic_input_cycles_active.max.pct_of_peak_sustained_elapsed",
+        "lts__d_atomic_input_cycles_active.min.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors.avg", "lts__t_sectors.max", "lts__t_sectors.min",
+        "lts__throughput.max.pct_of_peak_sustained_elapsed",
+        # issue and pipes (ALU-bound kernels)
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
 
 
 def to_bytes(val, unit):
