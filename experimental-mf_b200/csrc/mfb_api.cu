@@ -124,39 +124,54 @@ static void free_ds_device(Dataset* d) {
   d->d_uc = d->d_vc = d->d_last_u = d->d_last_v = nullptr;
 }
 
-int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) {
-  if (c->placement_done) return MFB_OK;
+int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode, bool planes) {
+  // Two searches, each run once when first needed: the plane-layout scratch copy the stream kernel works
+  // on during whole-epoch launches (planes), and the rows of phi themselves (chunked / multi-GPU epochs).
+  // bv is placed by whichever runs first.
+  const int which = planes ? 1 : 0;
+  if (c->placement_done[which]) return MFB_OK;
   const int trials = std::min(c->opt_placement_trials, 64);
   if (trials <= 1 || (mode != MFB_MODE_ATOMIC && mode != MFB_MODE_HOGWILD)) return MFB_OK;
   int64_t total = 0;
   for (int i = 0; i < nds; i++) total += ds[i]->nratings;
   if (total < c->placement_min_ratings) return MFB_OK;  // (not marked done: a larger file may follow)
-  c->placement_done = true;
+  c->placement_done[which] = true;
   const size_t phi_bytes = ((size_t)c->nv * c->stride + 15) / 16 * 16 * sizeof(float);
   const size_t bv_bytes = ((size_t)c->nv + 15) / 16 * 16 * sizeof(float);
-  const size_t slot = (phi_bytes + bv_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
-  float* const phi0 = c->arr[MFB_PHI];
-  float* const bv0 = c->arr[MFB_BV];
-  // candidate 0 is where the arrays are; the others are slots of ONE arena that stays allocated (a few
-  // hundred MB at most; freeing per candidate would cost more time than the calibration itself)
-  int n = trials;
-  char* arena = nullptr;
-  while (n > 1 && cudaMalloc(&arena, (size_t)(n - 1) * slot) != cudaSuccess) {
-    cudaGetLastError();
-    arena = nullptr;
-    n = (n + 1) / 2;
+  // a slot of the arena holds phi, bv and the plane-layout scratch copy; candidate 0 is the set of
+  // original allocations (kept: the second search starts from them again)
+  const size_t slot = (2 * phi_bytes + bv_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  if (!c->d_phi_planes) MFB_CUDA(cudaMalloc(&c->d_phi_planes, phi_bytes));
+  if (!c->placement_arena) {
+    int n = trials;
+    while (n > 1 && cudaMalloc(&c->placement_arena, (size_t)(n - 1) * slot) != cudaSuccess) {
+      cudaGetLastError();
+      c->placement_arena = nullptr;
+      n = (n + 1) / 2;
+    }
+    if (!c->placement_arena) return MFB_OK;
+    c->placement_slots = n;
+    c->place0[0] = c->arr[MFB_PHI];
+    c->place0[1] = c->arr[MFB_BV];
+    c->place0[2] = c->d_phi_planes;
   }
-  if (!arena) return MFB_OK;
-  auto phi_of = [&](int i) { return i == 0 ? phi0 : (float*)(arena + (size_t)(i - 1) * slot); };
-  auto bv_of = [&](int i) { return i == 0 ? bv0 : (float*)(arena + (size_t)(i - 1) * slot + phi_bytes); };
+  const int n = c->placement_slots;
+  char* const arena = c->placement_arena;
+  auto phi_of = [&](int i) { return i == 0 ? c->place0[0] : (float*)(arena + (size_t)(i - 1) * slot); };
+  auto bv_of = [&](int i) { return i == 0 ? c->place0[1] : (float*)(arena + (size_t)(i - 1) * slot + phi_bytes); };
+  auto planes_of = [&](int i) { return i == 0 ? c->place0[2] : (float*)(arena + (size_t)(i - 1) * slot + phi_bytes + bv_bytes); };
+  float* const phi_cur = c->arr[MFB_PHI];
+  float* const bv_cur = c->arr[MFB_BV];
+  const bool place_bv = !c->bv_placed;
   cudaEvent_t e0, e1;
   MFB_CUDA(cudaEventCreate(&e0));
   MFB_CUDA(cudaEventCreate(&e1));
   // the launch of the steady state: as wide as the run bound allows, deepest ring; probe off
   const int save_kernel = c->opt_kernel, save_ring = c->opt_ring, save_groups = c->opt_max_groups;
-  const bool save_timed = c->timed;
+  const bool save_timed = c->timed, save_allowed = c->planes_allowed;
   int* const save_version = c->d_version;
   c->d_version = nullptr;
+  c->planes_allowed = planes;
   int rc = MFB_OK;
   auto calibrate = [&](int divisor) {
     for (int i = 0; i < nds && rc == MFB_OK; i++) {
@@ -171,8 +186,9 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) 
     }
   };
   auto timed_run = [&](int i, int divisor, float* ms) -> int {
-    c->arr[MFB_PHI] = phi_of(i);
-    c->arr[MFB_BV] = bv_of(i);
+    if (planes) c->d_phi_planes = planes_of(i);
+    else c->arr[MFB_PHI] = phi_of(i);
+    if (place_bv) c->arr[MFB_BV] = bv_of(i);
     MFB_CUDA(cudaEventRecord(e0, c->stream));
     calibrate(divisor);
     MFB_CUDA(cudaEventRecord(e1, c->stream));
@@ -181,20 +197,23 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) 
     return rc;
   };
   calibrate(10);  // warm-up, not timed
-  for (int i = 1; i < n && rc == MFB_OK; i++) {
-    if (cudaMemcpyAsync(phi_of(i), phi0, phi_bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
-        cudaMemcpyAsync(bv_of(i), bv0, bv_bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
-      set_error("placement search: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int i = 0; i < n && rc == MFB_OK; i++) {  // every candidate gets the (unchanged) values
+    cudaError_t e = cudaSuccess;
+    if (!planes && phi_of(i) != phi_cur) e = cudaMemcpyAsync(phi_of(i), phi_cur, phi_bytes, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess && place_bv && bv_of(i) != bv_cur)
+      e = cudaMemcpyAsync(bv_of(i), bv_cur, bv_bytes, cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) {
+      set_error("placement search: device copy failed: %s", cudaGetErrorString(e));
       rc = MFB_E_CUDA;
     }
   }
   // stage 1: every candidate over the first tenth of the file(s); stage 2: the three fastest over the
-  // first two fifths (a short prefix sees the launch tail and a narrower mix of items)
+  // first fifth, twice (a short prefix sees the launch tail and a narrower mix of items)
   std::vector<std::pair<float, int>> order;
   for (int i = 0; i < n && rc == MFB_OK; i++) {
     float ms = 0.f;
     rc = timed_run(i, 10, &ms);
-    c->placement_ms[i] = ms;
+    c->placement_ms[which][i] = ms;
     order.push_back({ms, i});
   }
   int best = 0;
@@ -207,26 +226,24 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode) 
       rc = rc ? rc : timed_run(order[j].second, 5, &ms);
       if (j == 0 || ms < best_ms) { best = order[j].second; best_ms = ms; }
     }
-    c->placement_tried = n;
-    c->placement_best = best;
+    c->placement_tried[which] = n;
+    c->placement_best[which] = best;
   }
   c->opt_kernel = save_kernel;
   c->opt_ring = save_ring;
   c->opt_max_groups = save_groups;
   c->timed = save_timed;
+  c->planes_allowed = save_allowed;
   c->d_version = save_version;
   cudaStreamSynchronize(c->stream);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   // every candidate holds the same (unchanged) values: keep the fastest
-  c->arr[MFB_PHI] = phi_of(best);
-  c->arr[MFB_BV] = bv_of(best);
-  if (best == 0) {
-    cudaFree(arena);
-  } else {
-    c->placement_arena = arena;
-    cudaFree(phi0);
-    cudaFree(bv0);
+  if (planes) c->d_phi_planes = planes_of(best);
+  else c->arr[MFB_PHI] = phi_of(best);
+  if (place_bv) {
+    c->arr[MFB_BV] = bv_of(best);
+    c->bv_placed = true;
   }
   return rc;
 }
@@ -331,10 +348,13 @@ void mfb_destroy(mfb_ctx* h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& d : c->datasets) free_ds_device(&d);
-  if (c->placement_arena) {  // phi/bv live inside the arena of the placement search
-    c->arr[MFB_PHI] = c->arr[MFB_BV] = nullptr;
+  if (c->placement_arena) {  // phi/bv/plane scratch may live inside the arena of the placement search
+    c->arr[MFB_PHI] = c->place0[0];
+    c->arr[MFB_BV] = c->place0[1];
+    c->d_phi_planes = c->place0[2];
     cudaFree(c->placement_arena);
   }
+  cudaFree(c->d_phi_planes);
   for (auto& p : c->arr) cudaFree(p);
   cudaFree(c->d_counter);
   cudaFree(c->d_accum);
@@ -400,7 +420,8 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
     c->opt_batch = value;
   } else if (!strcmp(name, "phi_planes")) {
-    c->opt_phi_planes = value != 0;
+    MFB_REQUIRE(value >= 0 && value <= 2, "phi_planes must be 0 (rows), 1 (128-byte planes) or 2 (experiment: sector addressing)");
+    c->opt_phi_planes = value;
   } else if (!strcmp(name, "two_streams")) {
     c->opt_two_streams = value != 0;
   } else if (!strcmp(name, "epoch_launches")) {
@@ -674,14 +695,16 @@ int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mod
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC,
               "bad mode %d", mode);
   MFB_CUDA(cudaSetDevice(c->device));
-  if (int trc = tune_placement(c, &d, 1, gb, mode)) return trc;
+  if (int trc = tune_placement(c, &d, 1, gb, mode, c->opt_phi_planes == 1 && c->opt_epoch_launches <= 1 && c->stride == 128)) return trc;
   begin_timing(c);
   int rc = MFB_OK;
   const int64_t parts = std::max(1, c->opt_epoch_launches);  // diagnostic: the epoch as several launches
+  c->planes_allowed = true;  // this launch has the item matrix to itself: the stream kernel may transpose it
   for (int64_t k = 0; k < parts && rc == MFB_OK && d->nruns; k++) {
     const int64_t r0 = d->nruns * k / parts, r1 = d->nruns * (k + 1) / parts;
     if (r1 > r0) rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
   }
+  c->planes_allowed = false;
   end_timing(c);
   return rc;
 }
@@ -704,7 +727,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_CUDA(cudaSetDevice(c->device));
   if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   if (!d->refresh_pending) {  // (the tiles are resident from finalize: the calibration can use them)
-    if (int trc = tune_placement(c, &d, 1, gb, mode)) return trc;
+    if (int trc = tune_placement(c, &d, 1, gb, mode, false)) return trc;
   }
   if (chunk_ratings <= 0) chunk_ratings = 3 << 20;
   // Chunks grow geometrically by 7/4 up to 6x the given size: the first kernel starts after a small
@@ -1182,12 +1205,12 @@ float mfb_last_kernel_ms(mfb_ctx* h) {
 int64_t mfb_launch_count(mfb_ctx* h) { return h ? h->c.launches : 0; }
 int64_t mfb_h2d_bytes(mfb_ctx* h) { return h ? h->c.h2d_bytes : 0; }
 
-int mfb_placement_report(mfb_ctx* h, float* ms, int n, int* best) {
-  MFB_REQUIRE(h, "ctx is NULL");
+int mfb_placement_report(mfb_ctx* h, int which, float* ms, int n, int* best) {
+  MFB_REQUIRE(h && (which == 0 || which == 1), "bad argument");
   const Context* c = &h->c;
-  for (int i = 0; i < c->placement_tried && i < n; i++) ms[i] = c->placement_ms[i];
-  if (best) *best = c->placement_best;
-  return std::min(n, c->placement_tried);
+  for (int i = 0; i < c->placement_tried[which] && i < n; i++) ms[i] = c->placement_ms[which][i];
+  if (best) *best = c->placement_best[which];
+  return std::min(n, c->placement_tried[which]);
 }
 
 int mfb_last_launch(mfb_ctx* h, int out[4]) {

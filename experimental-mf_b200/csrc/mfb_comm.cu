@@ -160,7 +160,7 @@ int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, 
   const int P = m->world;
   MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[P] == c->nv, "item_bounds must span [0, nv]");
   MFB_CUDA(cudaSetDevice(c->device));
-  if (!c->placement_done) {  // placement of this rank's copy of the item matrix, over all of its cells
+  if (!c->placement_done[0]) {  // placement of this rank's copy of the item matrix, over all of its cells
     std::vector<Dataset*> cells;
     for (int b = 0; b < P; b++) {
       const int ds = datasets[b];
@@ -168,7 +168,7 @@ int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, 
       if (!c->datasets[ds].refresh_pending) cells.push_back(&c->datasets[ds]);
     }
     if ((int)cells.size() == P) {
-      if (int trc = tune_placement(c, cells.data(), P, gb, mode)) return trc;
+      if (int trc = tune_placement(c, cells.data(), P, gb, mode, false)) return trc;
     }
   }
   cudaEventRecord(c->ev0, c->stream);

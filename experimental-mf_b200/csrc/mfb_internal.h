@@ -120,7 +120,12 @@ struct Context {
                                 // (mfb_sgd_burst.cu); 0 = choose between 3 and 4
   int use_kernel = 3;           // ... the one chosen for the most recent epoch
   double rate_stream = 1.2e6, rate_burst = 5.0e6;  // updates/s per run in flight (measured; for the choice)
-  int opt_phi_planes = 0;       // experiment: plane addressing of the item matrix in the stream kernel
+  int opt_phi_planes = 0;       // stream kernel: 0 = rows; 1 = the item matrix as four 128-byte planes during whole-epoch
+                                // launches (transposed into d_phi_planes and back): narrows the spread over placements
+                                // (14.5..16.0 against 15.1..18.9 ms) but the searched rows are as fast (14.8..15.3 against
+                                // 14.9..16.0 ms after the search), so it is off; 2 = experiment (sector addressing only)
+  bool planes_allowed = false;  // set around launches that own the item matrix alone (mfb_sgd_epoch, calibration)
+  float* d_phi_planes = nullptr;  // scratch copy in plane layout; lives in the placement arena once the search ran
   int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
   int opt_epoch_launches = 1;   // diagnostic: mfb_sgd_epoch as this many launches over equal run ranges
   int opt_span_runs = 0;        // burst kernel: runs per claim (0 = by file size: 8, 16 or 32)
@@ -137,10 +142,13 @@ struct Context {
   int opt_placement_trials = 16; // candidate placements of the item matrix tried before the first parallel epoch
                                 // on a file of >= placement_min_ratings records (<= 1: off); tune_placement()
   int64_t placement_min_ratings = 4000000;
-  bool placement_done = false;
-  float placement_ms[64] = {0};  // diagnostic: calibration time of every candidate (mfb_placement_report)
-  int placement_tried = 0, placement_best = -1;
-  char* placement_arena = nullptr;  // holds phi/bv when a candidate other than the original allocation won
+  bool placement_done[2] = {false, false};  // [0] rows of phi, [1] plane-layout scratch (tune_placement)
+  bool bv_placed = false;
+  float placement_ms[2][64] = {{0}};  // diagnostic: stage-1 calibration time of every candidate (mfb_placement_report)
+  int placement_tried[2] = {0, 0}, placement_best[2] = {-1, -1};
+  char* placement_arena = nullptr;  // candidate slots 1..n-1 (phi, bv, plane scratch each); slot 0 = place0
+  int placement_slots = 0;
+  float* place0[3] = {nullptr, nullptr, nullptr};  // the original allocations of phi, bv, plane scratch
   int opt_admf_weight = 3;      // admf kernel: item rows a run counts for in the hot-row budget
   int opt_admf_prefetch = 1;    // admf kernel: next item row requested one record ahead
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
@@ -178,7 +186,7 @@ LaunchShape pick_launch(Context* c, const void* kernel, int lpr, int64_t groups_
 // allocations, runs the parallel SGD kernel with eta = 0 (increments of exactly zero: the model is
 // unchanged, the memory traffic is the real one) over the first fifth of every given dataset on each,
 // and keeps the fastest.  Once per context.
-int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode);
+int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode, bool planes);
 // kernels (mfb_sgd.cu)
 // runs [run_begin, run_end) of the dataset, in the given schedule
 int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mode,

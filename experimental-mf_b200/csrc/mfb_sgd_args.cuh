@@ -24,7 +24,10 @@ struct SgdArgs {
   // stream kernel: float4 index of (item v, this lane's vector i) = v*phi_row4 + i*phi_line4 + lane.
   // Rows as they are: (nvec, LPR).  Plane layout: (LPR, planes of nv*LPR float4) - the 128-byte lines
   // of one row then lie nv*128 bytes apart and hash to different L2 slices.
-  int64_t phi_row4, phi_line4;
+  // phi_pair4 != 0: lanes 2m, 2m+1 (one 32-byte sector) of a vector lie phi_pair4 float4 after those of
+  // lanes 2m-2, 2m-1 - the sector layout: plane j holds sector j of every item (32 bytes per item), so a
+  // row spreads over 16 chunks of 256 bytes and a chunk holds one sector of 8 consecutive items
+  int64_t phi_row4, phi_line4, phi_pair4;
   float eta, lameta, lm1, gb;
   int ld_flavour, st_flavour, bias_flavour;  // see mfb_group.cuh; bias: 0 red.add, 1 skip, 2 st.cg
   int throttle;  // streaming kernel: wait for the previous record's bias atomic before the next reductions

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
   const unsigned m = sub_mask<LPR>(lane);
   constexpr unsigned FULL = 0xffffffffu;
   const float4* __restrict__ phi4 = reinterpret_cast<const float4*>(a.phi);
+  const int64_t lane_off = a.phi_pair4 ? (int64_t)(gl >> 1) * a.phi_pair4 + (gl & 1) : (int64_t)gl;
   float4* theta4 = reinterpret_cast<float4*>(a.theta);
   bool ok[VPL];  // this lane's vector i exists (rows whose length is not a multiple of LPR*4 floats)
 #pragma unroll
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
       const int v = lds1i(chunk0 + cbuf * 256 + (sub * LPR + idx) * 4);
       fr[s] = lds1(chunk0 + cbuf * 256 + 128 + (sub * LPR + idx) * 4);
       fv[s] = v;
-      const float4* p = phi4 + (int64_t)v * a.phi_row4 + gl;
+      const float4* p = phi4 + (int64_t)v * a.phi_row4 + lane_off;
 #pragma unroll
       for (int i = 0; i < VPL; i++)
         if (ok[i]) cp_async16(ring_me + (s * 32 * VPL + i * LPR) * 16, p + i * a.phi_line4);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
         // while the L2 keeps up (the round trip overlaps a whole step).
         if (a.throttle) sink ^= __float_as_uint(ack[u & 1]);
         // the reductions come first: they end the window in which this row is stale elsewhere
-        float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)fv[s] * a.phi_row4 + gl;
+        float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)fv[s] * a.phi_row4 + lane_off;
         const float2 keep = (MODE == MFB_MODE_ATOMIC) ? lm12 : lameta2;  // increment vs new value
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
@@ -359,6 +360,30 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
     atomicAdd(a.probe_out + 1, pr_n);
     atomicAdd(a.probe_out + 2, pr_hsum);
     atomicAdd(a.probe_out + 3, pr_hn);
+  }
+}
+
+// Plane layout of the item matrix: plane i holds float4 [i*L, i*L+L) of every item, L
+// float4 (128 bytes for L = 8) per item - the pieces of one row lie nv*L*16 bytes apart and hash to
+// different L2 slices, and a 256-byte hash chunk holds pieces of two items, so a row's reductions are
+// spread over twice as many slices in pieces half as heavy.  The matrix is transposed into a scratch
+// copy before the kernel and back after it (9 MB each way: microseconds).
+__global__ void phi_rows_to_planes_kernel(const float4* __restrict__ rows, float4* __restrict__ planes, int nv,
+                                          int nvec, int L) {
+  const int64_t n = (int64_t)nv * nvec;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / nvec;
+    const int q = (int)(t - v * nvec), i = q / L, gl = q - i * L;
+    planes[v * L + (int64_t)i * nv * L + gl] = rows[t];
+  }
+}
+__global__ void phi_planes_to_rows_kernel(const float4* __restrict__ planes, float4* __restrict__ rows, int nv,
+                                          int nvec, int L) {
+  const int64_t n = (int64_t)nv * nvec;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / nvec;
+    const int q = (int)(t - v * nvec), i = q / L, gl = q - i * L;
+    rows[t] = planes[v * L + (int64_t)i * nv * L + gl];
   }
 }
 
@@ -404,9 +429,23 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * subs) / LPR);  // single runs at the end
   aa.phi_row4 = a.nvec;
   aa.phi_line4 = LPR;
-  if (c->opt_phi_planes && a.nvec == LPR * VPL) {  // EXPERIMENT: plane addressing without transposing the data
+  aa.phi_pair4 = 0;
+  if (c->opt_phi_planes == 2 && a.nvec == LPR * VPL) {  // EXPERIMENT: sector layout, addressing only
+    aa.phi_row4 = 2;
+    aa.phi_pair4 = (int64_t)c->nv * 2;
+    aa.phi_line4 = (int64_t)(LPR / 2) * aa.phi_pair4;
+  }
+  // production: 128-byte planes, for whole-epoch launches of rows that fill the lanes exactly
+  const bool planes = c->opt_phi_planes == 1 && c->planes_allowed && LPR == 8 && a.nvec == LPR * VPL;
+  const int tgrid = c->sm_count * 4;
+  if (planes) {
+    if (!c->d_phi_planes) MFB_CUDA(cudaMalloc(&c->d_phi_planes, (size_t)c->nv * c->stride * sizeof(float)));
+    phi_rows_to_planes_kernel<<<tgrid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(a.phi),
+                                                           reinterpret_cast<float4*>(c->d_phi_planes), c->nv, a.nvec, LPR);
+    aa.phi = c->d_phi_planes;
     aa.phi_row4 = LPR;
     aa.phi_line4 = (int64_t)c->nv * LPR;
+    c->launches++;
   }
   const int nspans = aa.big_spans + (nruns - aa.big_spans * LPR);
   // spread the warps over all SMs before stacking them: 1..4 warps per CTA
@@ -426,6 +465,11 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   c->last_ring = R;
   void* args[] = {(void*)&aa, (void*)&nspans};
   MFB_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), args, (size_t)(threads / 32) * WARP_BYTES, c->stream));
+  if (planes) {
+    phi_planes_to_rows_kernel<<<tgrid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_phi_planes),
+                                                           reinterpret_cast<float4*>(a.phi), c->nv, a.nvec, LPR);
+    c->launches++;
+  }
   MFB_CUDA(cudaGetLastError());
   c->launches++;
   return MFB_OK;

@@ -87,7 +87,7 @@ SIGNATURES = {
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
     "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
     "mfb_dsgd_timeline": (C.c_int, [C.c_void_p, f32p, C.c_int]),
-    "mfb_placement_report": (C.c_int, [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]),
+    "mfb_placement_report": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]),
     "mfb_comm_allgather_items": (C.c_int, [C.c_void_p, i32p]),
     "mfb_comm_allreduce_sse": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mfb_probe_arm": (C.c_int, [C.c_void_p, C.c_int]),
@@ -438,10 +438,14 @@ class Context:
         b = np.ascontiguousarray(item_bounds, np.int32)
         _check(lib().mfb_dsgd_epoch(self.h, ds, b.ctypes.data_as(i32p), eta, lam, gb, mode))
 
-    def placement_report(self):
-        """(calibration ms of every candidate placement of the item matrix, index of the one kept)"""
+    def placement_report(self, which=None):
+        """(calibration ms of every candidate placement, index of the one kept) for the plane-layout
+        working copy (which=1) or the rows of the item matrix (which=0); None = whichever search ran"""
+        if which is None:
+            a = self.placement_report(1)
+            return a if a[0] else self.placement_report(0)
         ms, best = np.zeros(64, np.float32), C.c_int(-1)
-        n = lib().mfb_placement_report(self.h, ms.ctypes.data_as(f32p), 64, C.byref(best))
+        n = lib().mfb_placement_report(self.h, which, ms.ctypes.data_as(f32p), 64, C.byref(best))
         return ms[:max(n, 0)].tolist(), best.value
 
     def dsgd_timeline(self, world):

@@ -265,10 +265,12 @@ int64_t mfb_launch_count(mfb_ctx* ctx);
 int64_t mfb_h2d_bytes(mfb_ctx* ctx);
 /* Placement search of the item matrix: before the first parallel SGD epoch on a file of
  * at least "placement_min_ratings" records (option, default 4,000,000) the library tries
- * "placement_trials" (option, default 16; <= 1 turns it off) allocations for phi/bv and keeps the fastest
- * - mfb_device_ptr(MFB_PHI / MFB_BV) may therefore change once, at that first epoch.  The report: ms[i] =
+ * "placement_trials" (option, default 16; <= 1 turns it off) locations and keeps the fastest - for the
+ * plane-layout working copy of phi that whole-epoch launches use (which = 1) and, on the first chunked or
+ * multi-GPU epoch, for the rows of phi themselves (which = 0); bv moves with the first search.
+ * mfb_device_ptr(MFB_PHI / MFB_BV) may therefore change at those epochs.  The report: ms[i] =
  * calibration time of candidate i, *best = the one kept; returns the number of candidates tried. */
-int mfb_placement_report(mfb_ctx* ctx, float* ms, int n, int* best);
+int mfb_placement_report(mfb_ctx* ctx, int which, float* ms, int n, int* best);
 /* shape of the most recent SGD epoch launch: out = {kernel variant, grid, threads per CTA, ring depth} */
 int mfb_last_launch(mfb_ctx* ctx, int out[4]);
 
