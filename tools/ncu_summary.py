@@ -21,6 +21,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__d_atomic_input_cycles_active.min.pct_of_peak_sustained_elapsed",
         "lts__t_sectors.avg", "lts__t_sectors.max", "lts__t_sectors.min",
         "lts__throughput.max.pct_of_peak_sustained_elapsed",
+        "lts__xbar2lts_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__xbar2lts_cycles_active.max.pct_of_peak_sustained_elapsed",
+        "lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_requests.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         # issue and pipes (ALU-bound kernels)
         "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
