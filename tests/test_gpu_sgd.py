@@ -124,6 +124,63 @@ def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim, kerne
     c.close()
 
 
+@pytest.mark.parametrize("planes", [0, 1])
+@pytest.mark.parametrize("mode", [mb.MODE_HOGWILD, mb.MODE_ATOMIC])
+def test_placement_search_and_plane_layout_leave_the_result_exact(mode, planes):
+    """before the first parallel epoch the library times the real kernel at eta = 0 on
+    candidate placements of the item matrix (rows, or the plane-layout working copy with
+    phi_planes = 1) and moves phi/bv to the fastest.  Property: the calibration leaves the model
+    untouched and the epochs that follow are the same epochs - on conflict-free data they equal
+    the serial oracle, two epochs in a row (the second one runs on the moved arrays)."""
+    n, dim = 20000, 128
+    rng = np.random.default_rng(7 + planes)
+    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1),
+                    rng.permutation(n), rng.integers(1, 6, n))
+    m = ol.Model(n, n, dim, seed=3, scale=0.3)
+    c = ctx_from_model(m)
+    c.set_option("row_concurrency", 0)
+    c.set_option("run_fraction_ppm", 0)
+    c.set_option("kernel", 3)
+    c.set_option("phi_planes", planes)
+    c.set_option("placement_trials", 5)
+    c.set_option("placement_min_ratings", 1000)
+    d = upload_ds(c, ds)
+    before = c.device_ptr(mb.PHI)
+    launches0 = c.launch_count()
+    for ep in (1, 2):
+        c.sgd_epoch(d, 0.05 / ep, 0.02, GB, mode)
+        oracle_sgd(m, ds, 0.05 / ep, 0.02, GB)
+        assert model_rel_err(c, m) <= 1e-5
+    ms, kept = c.placement_report(planes)
+    assert len(ms) == 5 and 0 <= kept < 5 and all(x > 0 for x in ms)
+    assert c.placement_report(1 - planes) == ([], -1)      # the other search did not run
+    # 1 warm-up + 5 candidates + 3 finalists twice = 12 calibration launches (x3 with the transposes)
+    assert c.launch_count() - launches0 >= 12 + 2
+    if planes == 0 and kept != 0:
+        assert c.device_ptr(mb.PHI) != before               # phi lives in the arena now
+    # and the search runs once
+    again = c.launch_count()
+    c.sgd_epoch(d, 0.01, 0.02, GB, mode)
+    assert c.launch_count() - again == (3 if planes else 1)
+    c.close()
+
+
+def test_placement_search_is_skipped_for_small_files_and_ordered_mode():
+    n, dim = 4000, 32
+    rng = np.random.default_rng(1)
+    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1),
+                    rng.permutation(n), rng.integers(1, 6, n))
+    m = ol.Model(n, n, dim, seed=3, scale=0.3)
+    c = ctx_from_model(m)
+    d = upload_ds(c, ds)
+    c.sgd_epoch(d, 0.05, 0.02, GB, mb.MODE_ATOMIC)         # 4,000 records < placement_min_ratings
+    assert c.placement_report(0) == ([], -1) and c.launch_count() == 1
+    c.set_option("placement_min_ratings", 0)
+    c.sgd_epoch(d, 0.05, 0.02, GB, mb.MODE_ORDERED)        # parity mode: never
+    assert c.placement_report(0) == ([], -1) and c.launch_count() == 2
+    c.close()
+
+
 def test_edge_cases_empty_and_ragged_runs():
     nu, nv, dim = 40, 70, 32
     m = ol.Model(nu, nv, dim, seed=1, scale=0.2)
