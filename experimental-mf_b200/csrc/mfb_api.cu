@@ -137,6 +137,9 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode, 
   if (total < c->placement_min_ratings) return MFB_OK;  // (not marked done: a larger file may follow)
   c->placement_done[which] = true;
   const size_t phi_bytes = ((size_t)c->nv * c->stride + 15) / 16 * 16 * sizeof(float);
+  // only a matrix that lives in the L2 is bound by its slices; a larger one (Yahoo shape: 320 MB) streams
+  // from HBM and would pay hundreds of MB of copies per candidate for nothing
+  if (phi_bytes > ((size_t)64 << 20)) return MFB_OK;
   const size_t bv_bytes = ((size_t)c->nv + 15) / 16 * 16 * sizeof(float);
   // a slot of the arena holds phi, bv and the plane-layout scratch copy; candidate 0 is the set of
   // original allocations (kept: the second search starts from them again)

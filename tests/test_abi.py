@@ -143,6 +143,32 @@ def test_wire_decoder_fast_path_and_general_path_agree(tmp_path):
         mb.Blocks.read(str(tmp_path / "short.bin"))
 
 
+def test_multi_frame_file_is_decoded_in_file_order_and_a_bad_frame_is_reported(tmp_path):
+    """The loader decodes the frames of a file on worker threads and stitches them in file order:
+    a file of many frames must come back exactly (block boundaries, run offsets, records), twice
+    in a row into the same arrays, and a malformed frame in the middle is an error that names it."""
+    import struct
+    tr, _, _ = mb.generate(mb.gen_params(3000, 400, 60000, users_per_block=20))
+    assert tr.nblocks > 100
+    path = str(tmp_path / "many.bin")
+    tr.write(path)
+    back = mb.Blocks.read(path)
+    for name in ("block_off", "run_uid", "run_off", "vid", "rating"):
+        np.testing.assert_array_equal(getattr(back, name), getattr(tr, name))
+    raw = bytearray(open(path, "rb").read())
+    # walk to frame 57 and break its first user message: length byte larger than the frame
+    off = 0
+    for _ in range(57):
+        off += 4 + struct.unpack_from("<I", raw, off)[0]
+    assert raw[off + 4] == 0x0A
+    raw[off + 5] = 0xFF
+    raw[off + 6] = 0x7F
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(mb.MfbError, match="malformed mf.Block at offset %d" % (off + 4)):
+        mb.Blocks.read(str(bad))
+
+
 def test_wire_roundtrip_agrees_with_oracle_codec(oracle_lib, tmp_path):
     train, test, _ = ol.make_ratings(200, 90, 5000, seed=12)
     p = train.write(str(tmp_path / "o.bin"))  # written by the oracle's encoder
