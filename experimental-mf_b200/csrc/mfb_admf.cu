@@ -48,6 +48,38 @@ struct AdmfArgs {
   float eta, eta_reg, gb;
 };
 
+// ---- cp.async (LDGSTS) staging of the item rows requested ahead -----------------------------------
+// A register ring does not pipeline (ptxas keeps all LDGs of a loop on one scoreboard slot, so the
+// first use of the oldest row waits for the newest request - DESIGN.md 3.1 item 4; measured here: the
+// row requested one record ahead by LDG gained 12 % per run).  The parallel schedule therefore lands the
+// rows of the next `depth` records in shared memory and retires them in order.
+constexpr int ADMF_RING = 4;  // slots per group; depth <= ADMF_RING - 1
+__device__ __forceinline__ void admf_cp16(uint32_t dst, const void* src) {  // L2 only (.cg): coherent with the reductions
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void admf_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void admf_wait(int depth) {  // all but the `depth` youngest groups have landed
+  if (depth <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else if (depth == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else if (depth == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+__device__ __forceinline__ float4 admf_lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int admf_lds1i(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float admf_lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ float link_fn(float x, int loss) {  // util.h:90-95
   return loss == 1 ? 1.0f / (1.0f + expf(-x)) : x;
 }
@@ -59,6 +91,14 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
   const int gl = lane & (LPR - 1);
   const unsigned m = group_mask<LPR>();
   if (ORDERED && (blockIdx.x != 0 || threadIdx.x >= LPR)) return;
+  // parallel schedule: ADMF_RING slots of (row, 16 bytes around the bias) per group in shared memory
+  extern __shared__ __align__(16) unsigned char admf_smem[];
+  constexpr int ROW_BYTES = LPR * VPL * 16;
+  constexpr int GROUP_BYTES = ADMF_RING * (ROW_BYTES + 16) + LPR * 8;  // ring + the chunk's item ids and ratings
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(admf_smem) + (uint32_t)(threadIdx.x / LPR) * GROUP_BYTES;
+  const uint32_t chunk_v = ring0 + ADMF_RING * (ROW_BYTES + 16), chunk_r = chunk_v + LPR * 4;
+  const int depth = a.prefetch;  // records requested ahead (0..ADMF_RING-1), uniform
+  const float4* const phi4 = reinterpret_cast<const float4*>(a.phi);
   float lam_u = 0.f, lam_v = 0.f, lam_bu = 0.f, lam_bv = 0.f;
   if (ORDERED) {
     lam_u = a.lams[0];
@@ -123,19 +163,61 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
         f_n = load_row<LPR, VPL>(a.phi, v_n, a.nvec, gl);
         bv_n = (gl == 0) ? __ldcg(a.bv + v_n) : 0.f;
       };
+      // parallel schedule: request the row of record (chunk position) q into slot q % ADMF_RING, or
+      // commit an empty group when the chunk / the run has no such record - the number of groups in
+      // flight is then always depth + 1 and the wait below takes a constant
+      auto request = [&](int j0, int q) {
+        if (q < LPR && j0 + q < hi) {
+          const int vq = admf_lds1i(chunk_v + q * 4);
+          const uint32_t slot = ring0 + (uint32_t)(q & (ADMF_RING - 1)) * (ROW_BYTES + 16);
+          const float4* src = phi4 + (int64_t)vq * a.nvec;
+#pragma unroll
+          for (int i = 0; i < VPL; i++) {
+            const int w = gl + i * LPR;
+            if (w < a.nvec) admf_cp16(slot + w * 16, src + w);
+          }
+          if (gl == 0) admf_cp16(slot + ROW_BYTES, a.bv + (vq & ~3));
+        }
+        admf_commit();
+      };
       for (int j = lo; j < hi; j++) {
         const int b = (j - lo) & (LPR - 1);
         if (b == 0) {
           const int q = j + gl;
           myvid = q < hi ? __ldcs(a.vid + q) : 0;
           myr = q < hi ? __ldcs(a.rating + q) : 0.f;
+          if (!ORDERED) {
+            // the chunk's item ids and ratings go to shared memory: reading record b's from there is one
+            // LDS, a sub-warp shuffle in this (divergent) loop is a ten-instruction protocol
+            __syncwarp(m);  // the previous chunk has been read by every lane of the group
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk_v + gl * 4), "r"(myvid) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(chunk_r + gl * 4), "f"(myr) : "memory");
+            __syncwarp(m);
+            for (int q0 = 0; q0 < depth; q0++) request(j, q0);
+          }
         }
-        if (ORDERED || !a.prefetch || b == 0) fetch(b);  // the ordered schedule reads every row after the previous update
-        const int v = v_n;
-        const float r = __shfl_sync(m, myr, b, LPR);
-        Row<VPL> f = f_n;
-        float bvv = __shfl_sync(m, bv_n, 0, LPR);
-        if (!ORDERED && a.prefetch && b + 1 < LPR && j + 1 < hi) fetch(b + 1);
+        int v;
+        Row<VPL> f;
+        float bvv;
+        if (ORDERED) {
+          fetch(b);  // the ordered schedule reads every row after the previous update
+          v = v_n;
+          f = f_n;
+          bvv = __shfl_sync(m, bv_n, 0, LPR);
+        } else {
+          request(j - b, b + depth);
+          admf_wait(depth);
+          v = admf_lds1i(chunk_v + b * 4);
+          const uint32_t slot = ring0 + (uint32_t)(b & (ADMF_RING - 1)) * (ROW_BYTES + 16);
+#pragma unroll
+          for (int i = 0; i < VPL; i++) {
+            const int w = gl + i * LPR;
+            f.v[i] = (w < a.nvec) ? admf_lds4(slot + w * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          bvv = (gl == 0) ? admf_lds1(slot + ROW_BYTES + (v & 3) * 4) : 0.f;
+          bvv = __shfl_sync(m, bvv, 0, LPR);
+        }
+        const float r = ORDERED ? __shfl_sync(m, myr, b, LPR) : admf_lds1(chunk_r + b * 4);
         t_prev = t;                                                    // admf.h:67
         bu_prev = bu;                                                  // admf.h:77
         store_row_f<LPR, VPL>(a.phi_old, v, a.nvec, gl, f, ORDERED ? 0 : 1);  // admf.h:68
@@ -177,7 +259,10 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
           }
           red_add_row<LPR, VPL>(a.phi, v, a.nvec, gl, df);
           if (gl == 0) {
-            atomicExch(a.bv_old + v, bvv);  // performed by the L2 atomic unit, like the reduction below
+            // the shadow value: a plain 4-byte store (an atomicExch - "performed by the L2 atomic unit like
+            // the reduction" - returns a value nobody reads and its round trip sat on the scoreboard:
+            // 51.9 -> 42.1 ms in epoch 1, 20.8 -> 17.5 ms at full width, same trajectory)
+            __stcg(a.bv_old + v, bvv);
             atomicAdd(a.bv + v, fmaf(cbv - 1.0f, bvv, e));
           }
           bu = fmaf(cbu, bu, e);
@@ -254,14 +339,18 @@ int launch_admf_t(Context* c, const Dataset* d, const AdmfArgs& a, int mode) {
   } else {
     auto k = admf_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC>;
     // The regularisers are learned from the same stale rows, which makes this path less tolerant than
-    // plain SGD; the step of a stale update is eta.  A run holds two item rows between gather and
-    // reduction (the current one and the one requested ahead); it counts for 3 in the hot-row budget
-    // (option admf_weight).  Measured at the Netflix shape, k = 64 (tools/exp_admf_width.py): weight
-    // 6 -> 3 halves the first epochs (102.7/54.0/37.8/29.7 -> 54.0/29.7/21.6/21.6 ms) and moves the
-    // test RMSE by <= 4e-4 and lam_bu by 0.5 %; weight 2: <= 6e-4 and 1.3 %; weight 1 without the
-    // row request ahead: 1.4e-3 and 3 %.  3,552 warps (registers) is the hardware limit.
-    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, c->opt_admf_weight, a.eta);
-    k<<<ls.grid, ls.threads, 0, c->stream>>>(a);
+    // plain SGD; the step of a stale update is eta.  A run holds depth + 1 item rows between gather and
+    // reduction (the current one and the `depth` requested ahead into shared memory); it counts for
+    // depth + 2 in the hot-row budget (option admf_weight overrides).  Measured at the Netflix shape,
+    // k = 64, with one row ahead (tools/exp_admf_width.py): weight 6 -> 3 halves the first epochs
+    // (102.7/54.0/37.8/29.7 -> 54.0/29.7/21.6/21.6 ms) and moves the test RMSE by <= 4e-4 and lam_bu by
+    // 0.5 %; weight 2: <= 6e-4 and 1.3 %.
+    AdmfArgs aa = a;
+    aa.prefetch = std::max(0, std::min(c->opt_admf_prefetch, ADMF_RING - 1));
+    const int weight = c->opt_admf_weight > 0 ? c->opt_admf_weight : aa.prefetch + 2;
+    const LaunchShape ls = pick_launch(c, (const void*)k, LPR, a.nruns, d->max_item_share, d->nruns, weight, a.eta);
+    const size_t smem = (size_t)(ls.threads / LPR) * (ADMF_RING * (LPR * VPL * 16 + 16) + LPR * 8);
+    k<<<ls.grid, ls.threads, smem, c->stream>>>(aa);
   }
   MFB_CUDA(cudaGetLastError());
   c->launches++;

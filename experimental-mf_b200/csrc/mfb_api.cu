@@ -456,10 +456,11 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value >= 0, "placement_min_ratings must be >= 0");
     c->placement_min_ratings = value;
   } else if (!strcmp(name, "admf_weight")) {
-    MFB_REQUIRE(value >= 1 && value <= 64, "admf_weight must be 1..64");
+    MFB_REQUIRE(value >= 0 && value <= 64, "admf_weight must be 0 (rows ahead + 2) or 1..64");
     c->opt_admf_weight = value;
   } else if (!strcmp(name, "admf_prefetch")) {
-    c->opt_admf_prefetch = value != 0;
+    MFB_REQUIRE(value >= 0 && value <= 3, "admf_prefetch must be 0..3 rows ahead");
+    c->opt_admf_prefetch = value;
   } else if (!strcmp(name, "memopt")) {
     c->opt_memopt = value;
   } else {

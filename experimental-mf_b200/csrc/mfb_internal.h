@@ -149,8 +149,9 @@ struct Context {
   char* placement_arena = nullptr;  // candidate slots 1..n-1 (phi, bv, plane scratch each); slot 0 = place0
   int placement_slots = 0;
   float* place0[3] = {nullptr, nullptr, nullptr};  // the original allocations of phi, bv, plane scratch
-  int opt_admf_weight = 3;      // admf kernel: item rows a run counts for in the hot-row budget
-  int opt_admf_prefetch = 1;    // admf kernel: next item row requested one record ahead
+  int opt_admf_weight = 0;      // admf kernel: item rows a run counts for in the hot-row budget (0 = depth + 2)
+  int opt_admf_prefetch = 1;    // admf kernel: item rows requested ahead of the record being worked on (0..3); more than
+                                // one gains nothing per run (251 warp instructions per step bound it) and costs width
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
   std::vector<Dataset> datasets;
