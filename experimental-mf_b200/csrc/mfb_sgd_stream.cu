@@ -332,7 +332,10 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
             __stcg(dst + i * a.phi_line4, nf);
           }
         }
-        if (gl == 0) ack[u & 1] = atom_add1(a.bv + fv[s], fmaf(a.lm1, bvv, e));
+        if (gl == 0) {
+          if (a.throttle) ack[u & 1] = atom_add1(a.bv + fv[s], fmaf(a.lm1, bvv, e));
+          else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a.bv + fv[s]), "f"(fmaf(a.lm1, bvv, e)) : "memory");
+        }
         if (a.version && gl == 0) {
           const int seen = atomicAdd(a.version + fv[s], 1) - fver[s];  // updates I did not see
           pr_sum += (unsigned)seen;
