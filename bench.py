@@ -236,7 +236,7 @@ def run_reference_arm(args, wl):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(wl, 1),
+        "data": "synthetic", "config": workload_config(wl, args.gpus),  # the config of the arm it stands beside
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference source + shim TBB/MKL/protobuf on the host CPU; each step = one epoch over the "
