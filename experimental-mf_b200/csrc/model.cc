@@ -439,12 +439,24 @@ void AdaptRegMF::admf_epoch() {
 // (the reference changes eta while earlier blocks may still be in flight; with --fly 1 the two
 // coincide).  The printed clock is cumulative since the first epoch started and, as in the
 // reference, includes the evaluation passes of earlier epochs.
+// MF_TIMING=1: where the start-up goes (stderr)
+static void lap(const char* what) {
+  static Time::time_point t0 = Time::now();
+  const Time::time_point t1 = Time::now();
+  if (getenv("MF_TIMING")) fprintf(stderr, "mf_b200: %-28s %.3f s\n", what, std::chrono::duration<float>(t1 - t0).count());
+  t0 = t1;
+}
+
 void run(MF& mf) {
+  lap("process start -> run()");
   mf.init();
+  lap("init (context, fill, mirrors)");
   if (mf.model_ != NULL) mf.read_model();
   mf::Blocks blocks_test;
   plain_read(mf.test_data_, blocks_test);
+  lap("test file");
   mf.load_train();
+  lap("training file (parse, ingest)");
   s = Time::now();
   for (int iter = 1; iter <= mf.iter_; iter++) {
     if (iter > 1) mf.seteta(iter);  // mf.h:38

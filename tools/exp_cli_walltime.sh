@@ -1,0 +1,24 @@
+#!/bin/bash
+# Drop-in comparison at the command line (GPU box): the same Netflix-shaped protobuf files, the same
+# flags, wall clock of the whole process (file parse, ingest, epochs, test RMSE per epoch):
+#   experimental-mf_b200/mf   --alg mf --iter 15      (this repo, one B200)
+#   oracle/_ref/mf_ref        --alg mf --iter 2       (the reference's own main() behind the shims, all host cores)
+set -e
+D=${TMPDIR:-/tmp}/mfb_cli_$$
+mkdir -p $D
+./experimental-mf_b200/getdata -w $D/nf --method synth --nu 480189 --nv 17770 --nnz 100000000 --test 0.01 | tail -1
+ls -la $D | awk '{print $5, $9}' | tail -2
+ARGS="--alg mf --train $D/nf.train --test $D/nf.test --nu 480189 --nv 17770 --dim 128 --eta 2e-2 --lambda 5e-3 --gam 1.0 --bias 2.76"
+for run in 1 2; do
+  s=$(date +%s%N)
+  MF_TIMING=1 MFB_TIMING=1 ./experimental-mf_b200/mf $ARGS --iter 15 --fly 8 > $D/ours.log 2>&1
+  grep "mf_b200:\|load_blocks" $D/ours.log
+  e=$(date +%s%N)
+  echo "mf (B200) 15 epochs, run $run: wall $(( (e - s) / 1000000 )) ms; last line: $(tail -1 $D/ours.log)"
+done
+C=$(nproc)
+s=$(date +%s%N)
+./oracle/_ref/mf_ref $ARGS --iter 2 --fly $C > $D/ref.log 2>&1
+e=$(date +%s%N)
+echo "mf_ref (reference source + shims, $C cores) 2 epochs: wall $(( (e - s) / 1000000 )) ms; last line: $(tail -1 $D/ref.log)"
+rm -rf $D
