@@ -775,7 +775,8 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
     MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
   }
   cudaStream_t const main_stream = c->stream;
-  const bool two = c->opt_two_streams != 0;
+  // (a file that fits the first chunk is one launch: nothing to overlap, so it keeps the full width)
+  const bool two = c->opt_two_streams != 0 && d->nratings > chunk_ratings;
   int rc = MFB_OK;
   int64_t r0 = 0;
   size_t chunk = 0;
