@@ -5,6 +5,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <sys/mman.h>
 
 #include "mfb_internal.h"
 
@@ -263,17 +266,69 @@ static void end_timing(Context* c) {
 
 using namespace mfb;
 
+// ---- host-side helpers of the ingest: the loops over all records run on all cores -----------------
+template <typename F>
+static void parallel_ranges(int64_t n, const F& fn) {  // fn(thread, begin, end) over [0, n) cut into equal parts
+  const int64_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const int64_t parts = std::max<int64_t>(1, std::min<int64_t>(hw, n / (1 << 16)));
+  std::vector<std::thread> pool;
+  for (int64_t t = 1; t < parts; t++) pool.emplace_back([&, t]() { fn((int)t, n * t / parts, n * (t + 1) / parts); });
+  fn(0, 0, n / parts);
+  for (auto& th : pool) th.join();
+}
+// first value outside [0, limit) or -1; *pos = its index
+static int64_t find_out_of_range(const int32_t* v, int64_t n, int32_t limit, int32_t* value) {
+  std::atomic<int64_t> bad(-1);
+  parallel_ranges(n, [&](int, int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; i++)
+      if ((uint32_t)v[i] >= (uint32_t)limit) {
+        int64_t cur = bad.load();
+        while ((cur < 0 || i < cur) && !bad.compare_exchange_weak(cur, i)) {}
+        return;
+      }
+  });
+  const int64_t at = bad.load();
+  if (at >= 0) *value = v[at];
+  return at;
+}
+template <typename T>
+static void append_parallel(std::vector<T>& dst, const std::vector<T>& src) {
+  const size_t base = dst.size();
+  if (src.empty()) return;
+  if (base != 0 || src.size() < ((size_t)1 << 20)) {
+    dst.insert(dst.end(), src.begin(), src.end());
+    return;
+  }
+  // an empty destination: first touch and copy by all threads (a serial insert() of 400 MB spends most
+  // of its time in page faults).  T is trivially copyable, so the elements may be written before the
+  // vector's size says they exist; resize() then value-initialises... which would zero them - so the
+  // vector is sized first over pre-faulted pages and filled afterwards.
+  dst.reserve(src.size());
+#ifdef MADV_POPULATE_WRITE
+  parallel_ranges((int64_t)src.size(), [&](int, int64_t b, int64_t e) {
+    const uintptr_t lo = ((uintptr_t)(dst.data() + b) + 4095) & ~(uintptr_t)4095, hi = (uintptr_t)(dst.data() + e) & ~(uintptr_t)4095;
+    if (hi > lo) madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE);
+  });
+#endif
+  dst.resize(src.size());
+  parallel_ranges((int64_t)src.size(), [&](int, int64_t b, int64_t e) { memcpy(dst.data() + b, src.data() + b, (size_t)(e - b) * sizeof(T)); });
+}
+
 static int append_host(Context* c, Dataset* d, const Dataset& src) {
   if (d->h_run_off.empty()) d->h_run_off.push_back(0);
   if (d->h_block_off.empty()) d->h_block_off.push_back(0);
   const int64_t base = (int64_t)d->h_vid.size(), rbase = (int64_t)d->h_run_uid.size();
   MFB_REQUIRE(base + (int64_t)src.h_vid.size() < (int64_t)INT32_MAX, "dataset too large for int32 offsets");
-  for (int32_t u : src.h_run_uid) MFB_REQUIRE(u >= 0 && u < c->nu, "uid %d outside [0,%d)", u, c->nu);
-  for (int32_t v : src.h_vid) MFB_REQUIRE(v >= 0 && v < c->nv, "vid %d outside [0,%d)", v, c->nv);
+  int32_t badv = 0;
+  MFB_REQUIRE(find_out_of_range(src.h_run_uid.data(), (int64_t)src.h_run_uid.size(), c->nu, &badv) < 0,
+              "uid %d outside [0,%d)", badv, c->nu);
+  MFB_REQUIRE(find_out_of_range(src.h_vid.data(), (int64_t)src.h_vid.size(), c->nv, &badv) < 0,
+              "vid %d outside [0,%d)", badv, c->nv);
   d->h_run_uid.insert(d->h_run_uid.end(), src.h_run_uid.begin(), src.h_run_uid.end());
+  d->h_run_off.reserve(d->h_run_off.size() + src.h_run_off.size());
   for (size_t r = 1; r < src.h_run_off.size(); r++) d->h_run_off.push_back((int32_t)(base + src.h_run_off[r]));
-  d->h_vid.insert(d->h_vid.end(), src.h_vid.begin(), src.h_vid.end());
-  d->h_rating.insert(d->h_rating.end(), src.h_rating.begin(), src.h_rating.end());
+  append_parallel(d->h_vid, src.h_vid);
+  append_parallel(d->h_rating, src.h_rating);
   for (size_t b = 1; b < src.h_block_off.size(); b++) d->h_block_off.push_back(rbase + src.h_block_off[b]);
   return MFB_OK;
 }
@@ -609,8 +664,11 @@ int mfb_dataset_load_file(mfb_ctx* h, int ds, const char* path) {
   MFB_REQUIRE(!d->finalized, "dataset %d already finalized", ds);
   int rc = load_blocks_file(path, d);
   if (rc) return rc;
-  for (int32_t u : d->h_run_uid) MFB_REQUIRE(u >= 0 && u < c->nu, "uid %d outside [0,%d) in %s", u, c->nu, path);
-  for (int32_t v : d->h_vid) MFB_REQUIRE(v >= 0 && v < c->nv, "vid %d outside [0,%d) in %s", v, c->nv, path);
+  int32_t badv = 0;
+  MFB_REQUIRE(find_out_of_range(d->h_run_uid.data(), (int64_t)d->h_run_uid.size(), c->nu, &badv) < 0,
+              "uid %d outside [0,%d) in %s", badv, c->nu, path);
+  MFB_REQUIRE(find_out_of_range(d->h_vid.data(), (int64_t)d->h_vid.size(), c->nv, &badv) < 0,
+              "vid %d outside [0,%d) in %s", badv, c->nv, path);
   return MFB_OK;
 }
 
@@ -632,9 +690,22 @@ int mfb_dataset_finalize(mfb_ctx* h, int ds) {
   if ((rc = to_device(c, d->h_vid, &d->d_vid))) return rc;
   if ((rc = to_device(c, d->h_rating, &d->d_rating))) return rc;
   {
-    std::vector<int32_t> cnt(c->nv, 0);
-    int32_t top = 0;
-    for (int32_t v : d->h_vid) top = std::max(top, ++cnt[v]);
+    // records of the most rated item: per-thread histograms over the records, merged
+    const int64_t hw = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::vector<int32_t>> part((size_t)hw);
+    parallel_ranges(d->nratings, [&](int t, int64_t b, int64_t e) {
+      std::vector<int32_t>& cnt = part[t];
+      cnt.assign(c->nv, 0);
+      const int32_t* v = d->h_vid.data();
+      for (int64_t i = b; i < e; i++) cnt[v[i]]++;
+    });
+    int64_t top = 0;
+    for (int32_t v = 0; v < c->nv; v++) {
+      int64_t sum = 0;
+      for (auto& cnt : part)
+        if (!cnt.empty()) sum += cnt[v];
+      top = std::max(top, sum);
+    }
     d->max_item_share = d->nratings ? (double)top / (double)d->nratings : 0.0;
   }
   if (c->arr[MFB_UR]) {  // dpmf enabled: static logical clock + per-row record counts
