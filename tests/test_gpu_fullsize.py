@@ -104,3 +104,33 @@ def test_streamed_epoch_equals_resident_epoch_at_full_size(data):
         c.close()
     tr.unpin()
     assert abs(got[0] - got[1]) <= 5e-4, got
+
+
+def test_admf_at_full_size_eta_zero_is_identity_and_one_epoch_learns(data):
+    """BASELINE configs[3] (adaptive regulariser, k=64) at full size through properties: with eta = 0
+    every record is visited and nothing moves - factors, biases and the four regularisers come back
+    bit for bit (the regularisers' step is eta_reg*eta); one real epoch then lowers the test RMSE
+    below the value the plain-SGD epoch 1 reaches and keeps the regularisers finite and >= 0."""
+    tr, te = data
+    k = 64
+    c = mb.Context(NU, NV, k)
+    c.init_normal(0x4D46B200, 1e-2)
+    c.enable(1)
+    c.snapshot_old()
+    dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+    vu = np.repeat(te.run_uid, np.diff(te.run_off)).astype(np.int32)   # the test file doubles as validation list
+    c.admf_set_validation(vu, te.vid, te.rating)
+    c.admf_set_lams([5e-3] * 4)
+    rng = np.random.default_rng(0)
+    c.admf_set_draws(rng.integers(0, len(vu), tr.nruns).astype(np.int32))
+    before, rmse0 = c.get_factors(), c.rmse(dte, GB)
+    c.admf_epoch(dtr, 0.0, 2e-2, 0, GB, mb.MODE_ATOMIC)
+    assert c.last_kernel_ms() > 1.0
+    for a, b in zip(before, c.get_factors()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(np.asarray(c.admf_get_lams(), np.float32), np.full(4, 5e-3, np.float32))
+    c.admf_epoch(dtr, 2e-2, 2e-2, 0, GB, mb.MODE_ATOMIC)
+    rmse1, lams = c.rmse(dte, GB), np.asarray(c.admf_get_lams())
+    assert rmse1 < 0.66 < rmse0, (rmse0, rmse1)
+    assert np.all(np.isfinite(lams)) and np.all(lams >= 0) and lams[2] > 5e-3   # lam_bu grows on this data
+    c.close()
