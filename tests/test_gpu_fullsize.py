@@ -134,3 +134,37 @@ def test_admf_at_full_size_eta_zero_is_identity_and_one_epoch_learns(data):
     assert rmse1 < 0.66 < rmse0, (rmse0, rmse1)
     assert np.all(np.isfinite(lams)) and np.all(lams >= 0) and lams[2] > 5e-3   # lam_bu grows on this data
     c.close()
+
+
+def test_sgld_noise_invariant_at_full_size(data):
+    """BASELINE configs[2] (SGLD, k=128, Philox noise) at full size through the invariant of SURVEY 8a3:
+    with the drift off, one epoch + flush adds independent N(0, temp*eta*ntrain) noise to EVERY
+    coordinate of EVERY row, however often the row is touched - 61 M user coordinates, 2.3 M item
+    coordinates, the 20 most rated items (0.47 % of the records each) against the least rated ones."""
+    tr, te = data
+    k = 128
+    c = mb.Context(NU, NV, k)          # factors, biases and lambda_u/lambda_v start at zero
+    c.enable(2)
+    d = c.dataset_from_blocks(tr)
+    ntrain = c.dp_weights(d)
+    assert ntrain == tr.nratings
+    c.upload(mb.UR, np.ones(NU, np.float32))
+    c.upload(mb.VR, np.ones(NV, np.float32))
+    eta, temp = np.float32(1e-9), np.float32(0.7)
+    p = mb.SgldParams(eta, temp, 1.0, ntrain, 0.0, 0.0, 0.0, 2024, 1, 0, 0)
+    c.sgld_epoch(d, p, GB, mb.MODE_HOGWILD)
+    c.sgld_flush_noise(d, p)
+    th, ph, bu, bv = c.get_factors()
+    c.close()
+    sd = np.sqrt(float(temp) * float(eta) * ntrain)
+    for name, a in (("theta", th), ("phi", ph), ("bu", bu), ("bv", bv)):
+        z = a.astype(np.float64).ravel() / sd
+        n = z.size
+        assert abs(z.mean()) < 5 / np.sqrt(n), (name, z.mean())
+        assert abs(z.var() - 1) < 0.01 + 4 * np.sqrt(2 / n), (name, z.var())
+        assert abs((z ** 4).mean() - 3) < 0.1 + 10 / np.sqrt(n), (name, (z ** 4).mean())
+    cnt = np.bincount(tr.vid, minlength=NV)
+    order = np.argsort(cnt)
+    hot, cold = ph[order[-20:]].astype(np.float64) / sd, ph[order[:200]].astype(np.float64) / sd
+    print("phi noise variance at full size: 20 most rated items %.3f, 200 least rated %.3f" % (hot.var(), cold.var()))
+    assert abs(hot.var() - 1) < 0.15 and abs(cold.var() - 1) < 0.05
