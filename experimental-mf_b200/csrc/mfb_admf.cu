@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
       float bu = (gl == 0) ? __ldcg(a.bu + uid) : 0.f;
       bu = __shfl_sync(m, bu, 0, LPR);
       float bu_prev = bu;
+      const Row<VPL> t_in = t;
+      const float bu_in = bu;
       const float cu = __fmul_rn(-a.eta, lam_u);                       // admf.h:73
       const float cv = __fsub_rn(1.0f, __fmul_rn(a.eta, lam_v));       // admf.h:75
       const float cbu = __fsub_rn(1.0f, __fmul_rn(a.eta, lam_bu));     // admf.h:79
@@ -268,10 +270,22 @@ __global__ void __launch_bounds__(256) admf_epoch_kernel(const AdmfArgs a) {
           bu = fmaf(cbu, bu, e);
         }
       }
-      store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
+      if (MODE == MFB_MODE_ATOMIC) {
+        // the user row receives what this run added to it as a reduction (a second run of the same user in
+        // flight in another group loses nothing); the shadow copy stays a plain store, as for items
+        Row<VPL> dt;
+#pragma unroll
+        for (int i = 0; i < VPL; i++)
+          dt.v[i] = make_float4(t.v[i].x - t_in.v[i].x, t.v[i].y - t_in.v[i].y, t.v[i].z - t_in.v[i].z,
+                                t.v[i].w - t_in.v[i].w);
+        red_add_row<LPR, VPL>(a.theta, uid, a.nvec, gl, dt);
+      } else {
+        store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
+      }
       store_row<LPR, VPL>(a.theta_old, uid, a.nvec, gl, t_prev);
       if (gl == 0) {
-        __stcg(a.bu + uid, bu);
+        if (MODE == MFB_MODE_ATOMIC) atomicAdd(a.bu + uid, bu - bu_in);
+        else __stcg(a.bu + uid, bu);
         __stcg(a.bu_old + uid, bu_prev);
       }
     }

@@ -472,7 +472,7 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
   } else if (!strcmp(name, "kernel")) {
-    MFB_REQUIRE(value >= 0 && value <= 4, "kernel must be 0 (choose), 1, 2, 3 or 4");
+    MFB_REQUIRE(value == 0 || value == 1 || value == 3 || value == 4, "kernel must be 0 (choose), 1 (generic), 3 (stream) or 4 (burst)");
     c->opt_kernel = value;
   } else if (!strcmp(name, "batch")) {
     MFB_REQUIRE(value == 4 || value == 8, "batch must be 4 or 8");
@@ -755,6 +755,10 @@ int64_t mfb_dataset_num_ratings(mfb_ctx* h, int ds) {
   Dataset* d = h ? get_ds(&h->c, ds) : nullptr;
   return d ? (d->finalized ? d->nratings : (int64_t)d->h_vid.size()) : -1;
 }
+int64_t mfb_dataset_num_blocks(mfb_ctx* h, int ds) {
+  Dataset* d = h ? get_ds(&h->c, ds) : nullptr;
+  return d ? (int64_t)d->h_block_off.size() - 1 : -1;
+}
 int64_t mfb_dataset_num_runs(mfb_ctx* h, int ds) {
   Dataset* d = h ? get_ds(&h->c, ds) : nullptr;
   return d ? (d->finalized ? d->nruns : (int64_t)d->h_run_uid.size()) : -1;
@@ -780,6 +784,26 @@ int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mod
     if (r1 > r0) rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
   }
   c->planes_allowed = false;
+  end_timing(c);
+  return rc;
+}
+
+// SgdFilter::operator() over Blocks [block_begin, block_end) of the file only (mf.h:76 is called once per
+// Block): a slice of an epoch.  The concurrency bounds are those of the whole file.
+int mfb_sgd_epoch_blocks(mfb_ctx* h, int ds, int64_t block_begin, int64_t block_end, float eta, float lambda,
+                         float gb, int mode) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Dataset* d = get_ds(c, ds);
+  if (!d) return MFB_E_ARG;
+  MFB_REQUIRE(d->finalized, "dataset %d not finalized", ds);
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC, "bad mode %d", mode);
+  MFB_REQUIRE(block_begin >= 0 && block_begin <= block_end && block_end <= d->nblocks, "blocks [%lld, %lld) outside 0..%lld",
+              (long long)block_begin, (long long)block_end, (long long)d->nblocks);
+  MFB_CUDA(cudaSetDevice(c->device));
+  begin_timing(c);
+  const int64_t r0 = d->h_block_off[block_begin], r1 = d->h_block_off[block_end];
+  int rc = r1 > r0 ? launch_sgd(c, d, eta, lambda, gb, mode, r0, r1) : MFB_OK;
   end_timing(c);
   return rc;
 }

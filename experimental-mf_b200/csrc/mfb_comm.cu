@@ -16,6 +16,8 @@
 
 #include "mfb_internal.h"
 
+#define MFB_MAX_HALVES 4
+
 namespace mfb {
 
 // NCCL is bound at run time (dlopen), not at link time: the library then loads on machines
@@ -70,7 +72,8 @@ struct Comm {
   ncclComm_t nccl = nullptr;
   int rank = 0, world = 1;
   cudaStream_t stream = nullptr;
-  cudaEvent_t computed = nullptr, shifted = nullptr;
+  cudaEvent_t computed[MFB_MAX_HALVES] = {nullptr}, shifted[MFB_MAX_HALVES] = {nullptr};
+  bool shift_pending[MFB_MAX_HALVES] = {false};
   double* d_red = nullptr;  // [2] sse, count
   // diagnostic timeline of the most recent epoch (mfb_dsgd_timeline): events on the compute stream
   // at the start of the epoch, after every cell kernel and after every wait for the ring shift
@@ -105,8 +108,10 @@ int mfb_comm_init(mfb_ctx* h, int rank, int world, const void* id128) {
   memcpy(&id, id128, sizeof id);
   MFB_NCCL(g_nccl.CommInitRank(&m->nccl, world, id, rank));
   MFB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  MFB_CUDA(cudaEventCreateWithFlags(&m->computed, cudaEventDisableTiming));
-  MFB_CUDA(cudaEventCreateWithFlags(&m->shifted, cudaEventDisableTiming));
+  for (int i = 0; i < MFB_MAX_HALVES; i++) {
+    MFB_CUDA(cudaEventCreateWithFlags(&m->computed[i], cudaEventDisableTiming));
+    MFB_CUDA(cudaEventCreateWithFlags(&m->shifted[i], cudaEventDisableTiming));
+  }
   MFB_CUDA(cudaMalloc(&m->d_red, 2 * sizeof(double)));
   c->comm = m;
   return MFB_OK;
@@ -122,8 +127,10 @@ int mfb_comm_destroy(mfb_ctx* h) {
   cudaStreamSynchronize(c->stream);
   if (m->nccl) g_nccl.CommDestroy(m->nccl);
   for (cudaEvent_t e : m->marks) cudaEventDestroy(e);
-  cudaEventDestroy(m->computed);
-  cudaEventDestroy(m->shifted);
+  for (int i = 0; i < MFB_MAX_HALVES; i++) {
+    cudaEventDestroy(m->computed[i]);
+    cudaEventDestroy(m->shifted[i]);
+  }
   cudaStreamDestroy(m->stream);
   cudaFree(m->d_red);
   delete m;
@@ -131,78 +138,115 @@ int mfb_comm_destroy(mfb_ctx* h) {
   return MFB_OK;
 }
 
-// ring shift of one item block: send rows [bounds[b], bounds[b+1]) of phi/bv to rank-1, receive
-// block nb from rank+1.  Runs on the comm stream after the compute stream reached `computed`.
-static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb) {
+// Ring shift of one item block, asynchronous to the compute stream: after the compute stream reached the
+// point where this is called (the cell kernel on block `b` has been queued), the comm stream sends rows
+// [bounds[b], bounds[b+1]) of phi/bv to rank-1 and receives block `nb` from rank+1.  The compute stream does
+// NOT wait here: the kernel that next touches block nb waits for m->shifted[slot] (wait_shift).
+static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb, int slot) {
   const int P = m->world;
   const int to = (m->rank + P - 1) % P, from = (m->rank + 1) % P;
   const int64_t s0 = bounds[b], s1 = bounds[b + 1], r0 = bounds[nb], r1 = bounds[nb + 1];
-  MFB_CUDA(cudaEventRecord(m->computed, c->stream));
-  MFB_CUDA(cudaStreamWaitEvent(m->stream, m->computed, 0));
+  MFB_CUDA(cudaEventRecord(m->computed[slot], c->stream));
+  MFB_CUDA(cudaStreamWaitEvent(m->stream, m->computed[slot], 0));
   MFB_NCCL(g_nccl.GroupStart());
   MFB_NCCL(g_nccl.Send(c->arr[MFB_PHI] + s0 * c->stride, (size_t)(s1 - s0) * c->stride, ncclFloat, to, m->nccl, m->stream));
   MFB_NCCL(g_nccl.Send(c->arr[MFB_BV] + s0, (size_t)(s1 - s0), ncclFloat, to, m->nccl, m->stream));
   MFB_NCCL(g_nccl.Recv(c->arr[MFB_PHI] + r0 * c->stride, (size_t)(r1 - r0) * c->stride, ncclFloat, from, m->nccl, m->stream));
   MFB_NCCL(g_nccl.Recv(c->arr[MFB_BV] + r0, (size_t)(r1 - r0), ncclFloat, from, m->nccl, m->stream));
   MFB_NCCL(g_nccl.GroupEnd());
-  MFB_CUDA(cudaEventRecord(m->shifted, m->stream));
-  MFB_CUDA(cudaStreamWaitEvent(c->stream, m->shifted, 0));
+  MFB_CUDA(cudaEventRecord(m->shifted[slot], m->stream));
+  m->shift_pending[slot] = true;
+  return MFB_OK;
+}
+static int wait_shift(Context* c, Comm* m, int slot) {
+  if (m->shift_pending[slot]) MFB_CUDA(cudaStreamWaitEvent(c->stream, m->shifted[slot], 0));
+  m->shift_pending[slot] = false;
   return MFB_OK;
 }
 
-int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
-                   float gb, int mode) {
+// One DSGD epoch.  Items are cut into P*H blocks (H = `halves` pieces of each rank's home block); datasets[j]
+// holds this rank's ratings with an item in block j.  The epoch is `rotations` turns of the ring; turn r works on
+// slice r of every cell (the source file cut into `rotations` runs of consecutive Blocks - a cell keeps the Block
+// structure of the file it was split from).  Sub-epoch s of a turn: for h = 0..H-1 the kernel on piece h of block
+// (rank+s) mod P, then - on the comm stream, overlapped with the kernel on piece h+1 - the shift of that piece.
+//  * H = 2 (default of the host programs) hides the exchange and the neighbour's lag of up to half a sub-epoch
+//    behind compute (SURVEY 8e "splitting each item block in two halves");
+//  * rotations > 1 in the FIRST epoch keeps the multi-GPU result on the reference's trajectory: the cost of the
+//    DSGD order in test RMSE is paid in epoch 1 only, while the factors leave their random initialisation and
+//    every (user shard, item block) pair has to agree on the latent basis; the ring turning 16 times in that
+//    epoch mixes the pairs 16 times as often (tools/dsgd_order_study.py: P = 8, final tRMSE +0.0142 with one
+//    turn in every epoch, +0.0007 with 16 turns in epoch 1 and one afterwards).
+int mfb_dsgd_epoch_ex(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, int halves, int rotations,
+                      float eta, float lambda, float gb, int mode) {
   MFB_REQUIRE(h && datasets && item_bounds, "NULL argument");
   Context* c = &h->c;
   Comm* m = (Comm*)c->comm;
   MFB_REQUIRE(m, "communicator not initialised");
   MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ATOMIC || mode == MFB_MODE_ORDERED, "bad mode");
-  const int P = m->world;
-  MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[P] == c->nv, "item_bounds must span [0, nv]");
+  MFB_REQUIRE(halves >= 1 && halves <= MFB_MAX_HALVES, "halves must be 1..%d", MFB_MAX_HALVES);
+  MFB_REQUIRE(rotations >= 1 && rotations <= 4096, "rotations must be 1..4096");
+  const int P = m->world, H = halves, NB = P * H;
+  MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[NB] == c->nv, "item_bounds must span [0, nv] in world*halves blocks");
   MFB_CUDA(cudaSetDevice(c->device));
-  if (!c->placement_done[0]) {  // placement of this rank's copy of the item matrix, over all of its cells
-    std::vector<Dataset*> cells;
-    for (int b = 0; b < P; b++) {
-      const int ds = datasets[b];
-      MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].finalized, "bad dataset for block %d", b);
-      if (!c->datasets[ds].refresh_pending) cells.push_back(&c->datasets[ds]);
-    }
-    if ((int)cells.size() == P) {
-      if (int trc = tune_placement(c, cells.data(), P, gb, mode, false)) return trc;
-    }
+  std::vector<Dataset*> cells(NB);
+  bool resident = true;
+  for (int j = 0; j < NB; j++) {
+    const int ds = datasets[j];
+    MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].finalized, "bad dataset for block %d", j);
+    cells[j] = &c->datasets[ds];
+    resident = resident && !cells[j]->refresh_pending;
+  }
+  // placement of this rank's copy of the item matrix, over all of its cells
+  if (!c->placement_done[0] && resident) {
+    if (int trc = tune_placement(c, cells.data(), NB, gb, mode, false)) return trc;
   }
   cudaEventRecord(c->ev0, c->stream);
-  if ((int)m->marks.size() < 2 * P + 1) {
+  const int nmarks = 2 * P * H * rotations + 1;
+  if ((int)m->marks.size() < nmarks) {
     const size_t old = m->marks.size();
-    m->marks.resize(2 * P + 1);
+    m->marks.resize(nmarks);
     for (size_t i = old; i < m->marks.size(); i++) MFB_CUDA(cudaEventCreate(&m->marks[i]));
   }
   m->nmarks = 0;
   MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
-  for (int s = 0; s < P; s++) {
-    const int b = (m->rank + s) % P, nb = (b + 1) % P;
-    const int ds = datasets[b];
-    MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].finalized, "bad dataset for block %d", b);
-    Dataset* d = &c->datasets[ds];
-    if (d->nruns) {
-      int rc = launch_sgd(c, d, eta, lambda, gb, mode, 0, d->nruns);
-      if (rc) return rc;
+  for (int r = 0; r < rotations; r++) {
+    for (int s = 0; s < P; s++) {
+      for (int hh = 0; hh < H; hh++) {
+        const int b = ((m->rank + s) % P) * H + hh, nb = ((m->rank + s + 1) % P) * H + hh;
+        Dataset* d = cells[b];
+        // the previous shift of this piece slot delivered the rows this kernel works on
+        if (int rc = wait_shift(c, m, hh)) return rc;
+        MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
+        const int64_t k0 = d->nblocks * r / rotations, k1 = d->nblocks * (r + 1) / rotations;
+        const int64_t r0 = d->h_block_off[k0], r1 = d->h_block_off[k1];
+        if (r1 > r0) {
+          int rc = launch_sgd(c, d, eta, lambda, gb, mode, r0, r1);
+          if (rc) return rc;
+        }
+        MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
+        if (P > 1) {
+          int rc = shift_block(c, m, item_bounds, b, nb, hh);
+          if (rc) return rc;
+        }
+      }
     }
-    MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
-    if (P > 1) {
-      int rc = shift_block(c, m, item_bounds, b, nb);
-      if (rc) return rc;
-    }
-    MFB_CUDA(cudaEventRecord(m->marks[m->nmarks++], c->stream));
   }
+  for (int hh = 0; hh < H; hh++)  // every block is home again before anything else uses the item matrix
+    if (int rc = wait_shift(c, m, hh)) return rc;
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;
   return MFB_OK;
 }
 
-// Diagnostic: where the most recent mfb_dsgd_epoch spent its time on this rank.  out[2s] = ms of the
-// cell kernel of sub-epoch s, out[2s+1] = ms the compute stream then waited for the ring shift (send of
-// the block just updated + arrival of the next one, i.e. also the neighbour's cell still running).
+int mfb_dsgd_epoch(mfb_ctx* h, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
+                   float gb, int mode) {
+  return mfb_dsgd_epoch_ex(h, datasets, item_bounds, 1, 1, eta, lambda, gb, mode);
+}
+
+// Diagnostic: where the most recent DSGD epoch spent its time on this rank.  Steps i = 0, 1, ... are the
+// (turn, sub-epoch, piece) kernels in launch order: out[2i] = ms the compute stream waited before kernel i
+// for the arrival of its item rows (the ring shift issued one sub-epoch earlier: the neighbour's kernel on
+// that piece + the transfer), out[2i+1] = ms of kernel i.
 int mfb_dsgd_timeline(mfb_ctx* h, float* out, int n) {
   MFB_REQUIRE(h && out, "NULL argument");
   Context* c = &h->c;

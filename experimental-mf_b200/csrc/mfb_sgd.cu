@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(256) sgd_epoch_kernel(const SgdArgs a) {
     } else {
       bu = __ldcg(a.bu + uid);
     }
+    const Row<VPL> t_in = t;
+    const float bu_in = bu;
     for (int j0 = lo; j0 < hi; j0 += LPR) {
       const int nb = min(LPR, hi - j0);
       int myvid = 0;
@@ -154,155 +156,20 @@ __global__ void __launch_bounds__(256) sgd_epoch_kernel(const SgdArgs a) {
         }
       }
     }
-    store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
-    if (gl == 0) __stcg(a.bu + uid, bu);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Batched variant of the parallel schedule for rows of one float4 per lane (stride 68..128).
-//
-// The sequential kernel above spends most of a rating inside one dependent chain (4 FMAs -> 5
-// shuffle rounds -> residual -> 8 FMAs) with 3 warps per scheduler to hide it (the concurrency
-// bound keeps the grid small).  Here 4 consecutive records of a run are updated together, with the
-// same result as updating them one after the other in exact arithmetic:
-//     theta^b = lameta*theta^(b-1) + e_b*phi_b   =>   <theta^(b-1), phi_b> =
-//         lameta^(b-1) <theta^0,phi_b> + sum_{a<b} lameta^(b-1-a) e_a <phi_a,phi_b>
-// so the 4 + 6 inner products <theta^0,phi_b>, <phi_a,phi_b> are reduced TOGETHER (independent
-// shuffles, 5 rounds for all of them), the residuals e_1..e_4 follow from a scalar recurrence that
-// every lane evaluates redundantly, and the row updates are straight vector FMAs + reductions.
-// The item rows of the NEXT batch are gathered while the current one is being computed.
-// (Records of one run are distinct items - getdata.cc groups a user's ratings, no (u,i) repeats.)
-__device__ __forceinline__ float4 load_phi4(const SgdArgs& a, int v, int gl, bool lane_ok) {
-  const float4* p = reinterpret_cast<const float4*>(a.phi) + (int64_t)v * a.nvec + gl;
-  if (!lane_ok) return make_float4(0.f, 0.f, 0.f, 0.f);
-  return a.ld_flavour == 0 ? __ldcg(p) : (a.ld_flavour == 1 ? *p : ld_na(p));
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256) sgd_epoch_kernel_b4(const SgdArgs a) {
-  constexpr int LPR = 32, VPL = 1, B = 4;
-  const int gl = threadIdx.x & 31;
-  const unsigned m = 0xffffffffu;
-  for (;;) {
-    int run;
-    if (gl == 0) run = a.run_begin + atomicAdd(a.counter, 1);
-    run = __shfl_sync(m, run, 0);
-    if (run >= a.nruns) break;
-    const int uid = __ldg(a.run_uid + run);
-    const int lo = __ldg(a.run_off + run), hi = __ldg(a.run_off + run + 1);
-    if (lo == hi) continue;
-    const bool lane_ok = gl < a.nvec;
-    float4 t = lane_ok ? __ldcg(reinterpret_cast<const float4*>(a.theta) + (int64_t)uid * a.nvec + gl)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    float bu = __ldcg(a.bu + uid);
-    for (int j0 = lo; j0 < hi; j0 += 32) {
-      const int nb = min(32, hi - j0);
-      int myvid = 0;
-      float myr = 0.f;
-      if (gl < nb) {
-        myvid = __ldcs(a.vid + j0 + gl);
-        myr = __ldcs(a.rating + j0 + gl);
-      }
-      const int nfull = nb & ~(B - 1);
-      float4 fn[B];
-      float bvn[B];
-      int vn[B];
-      if (nfull) {
+    if (MODE == MFB_MODE_ATOMIC) {
+      // the user row receives what this run added to it, as a reduction: a run of the same user in flight in
+      // another group at the same time then loses nothing (its row is merely stale, like an item row)
+      Row<VPL> dt;
 #pragma unroll
-        for (int b = 0; b < B; b++) {
-          vn[b] = __shfl_sync(m, myvid, b);
-          fn[b] = load_phi4(a, vn[b], gl, lane_ok);
-          bvn[b] = __ldcg(a.bv + vn[b]);
-        }
-      }
-      for (int b0 = 0; b0 < nfull; b0 += B) {
-        float4 f[B];
-        float bvv[B], r[B];
-        int v[B];
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-          f[b] = fn[b];
-          bvv[b] = bvn[b];
-          v[b] = vn[b];
-          r[b] = __shfl_sync(m, myr, b0 + b);
-        }
-        if (b0 + B < nfull) {  // gather the next batch now; it lands while this one is computed
-#pragma unroll
-          for (int b = 0; b < B; b++) {
-            vn[b] = __shfl_sync(m, myvid, b0 + B + b);
-            fn[b] = load_phi4(a, vn[b], gl, lane_ok);
-            bvn[b] = __ldcg(a.bv + vn[b]);
-          }
-        }
-        // 4 + 6 partial inner products per lane
-        float D[B], G[B][B];
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-          D[b] = fmaf(t.w, f[b].w, fmaf(t.z, f[b].z, fmaf(t.y, f[b].y, t.x * f[b].x)));
-#pragma unroll
-          for (int c = b + 1; c < B; c++)
-            G[b][c] = fmaf(f[b].w, f[c].w, fmaf(f[b].z, f[c].z, fmaf(f[b].y, f[c].y, f[b].x * f[c].x)));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // all ten reductions advance together
-#pragma unroll
-          for (int b = 0; b < B; b++) {
-            D[b] += __shfl_xor_sync(m, D[b], o);
-#pragma unroll
-            for (int c = b + 1; c < B; c++) G[b][c] += __shfl_xor_sync(m, G[b][c], o);
-          }
-        }
-        float coef[B];
-        float tpow = 1.0f;
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-          float d = tpow * D[b];
-#pragma unroll
-          for (int c = 0; c < b; c++) d = fmaf(coef[c], G[c][b], d);
-          const float e = a.eta * (r[b] - d - bu - bvv[b] - a.gb);
-          // increment of phi_b uses theta BEFORE this record's update
-          float4 nf;
-          if (MODE == MFB_MODE_ATOMIC) {
-            nf = make_float4(fmaf(e, t.x, a.lm1 * f[b].x), fmaf(e, t.y, a.lm1 * f[b].y),
-                             fmaf(e, t.z, a.lm1 * f[b].z), fmaf(e, t.w, a.lm1 * f[b].w));
-          } else {
-            nf = make_float4(fmaf(e, t.x, a.lameta * f[b].x), fmaf(e, t.y, a.lameta * f[b].y),
-                             fmaf(e, t.z, a.lameta * f[b].z), fmaf(e, t.w, a.lameta * f[b].w));
-          }
-          t = make_float4(fmaf(e, f[b].x, a.lameta * t.x), fmaf(e, f[b].y, a.lameta * t.y),
-                          fmaf(e, f[b].z, a.lameta * t.z), fmaf(e, f[b].w, a.lameta * t.w));
-          float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)v[b] * a.nvec + gl;
-          if (lane_ok) {
-            if (MODE == MFB_MODE_ATOMIC)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(nf.x), "f"(nf.y),
-                           "f"(nf.z), "f"(nf.w)
-                           : "memory");
-            else
-              __stcg(dst, nf);
-          }
-          if (gl == 0) atomicAdd(a.bv + v[b], fmaf(a.lm1, bvv[b], e));
-          bu = fmaf(a.lameta, bu, e);
-#pragma unroll
-          for (int c = 0; c < b; c++) coef[c] *= a.lameta;
-          coef[b] = e;
-          tpow *= a.lameta;
-        }
-      }
-      // tail of the lane-batch: fewer than 4 records, one at a time
-      for (int b = nfull; b < nb; b++) {
-        const int v = __shfl_sync(m, myvid, b);
-        const float r = __shfl_sync(m, myr, b);
-        Row<VPL> f = load_row<LPR, VPL>(a.phi, v, a.nvec, gl);
-        const float bvv = __ldcg(a.bv + v);
-        Row<VPL> tt;
-        tt.v[0] = t;
-        sgd_update_fast<LPR, VPL, MODE>(a, tt, bu, f, bvv, v, r, gl, m);
-        t = tt.v[0];
-      }
+      for (int i = 0; i < VPL; i++)
+        dt.v[i] = make_float4(t.v[i].x - t_in.v[i].x, t.v[i].y - t_in.v[i].y, t.v[i].z - t_in.v[i].z,
+                              t.v[i].w - t_in.v[i].w);
+      red_add_row<LPR, VPL>(a.theta, uid, a.nvec, gl, dt);
+      if (gl == 0) atomicAdd(a.bu + uid, bu - bu_in);
+    } else {
+      store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
+      if (gl == 0) __stcg(a.bu + uid, bu);
     }
-    if (lane_ok) __stcg(reinterpret_cast<float4*>(a.theta) + (int64_t)uid * a.nvec + gl, t);
-    if (gl == 0) __stcg(a.bu + uid, bu);
   }
 }
 
@@ -425,12 +292,8 @@ int launch_sgd_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
     constexpr int B = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
     const void* k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_ATOMIC, B>
                                             : (const void*)sgd_epoch_kernel<LPR, VPL, MFB_MODE_HOGWILD, B>;
-    const bool b4 = LPR == 32 && VPL == 1 && c->use_kernel == 2;  // the batched kernel above
-    if (b4)
-      k = mode == MFB_MODE_ATOMIC ? (const void*)sgd_epoch_kernel_b4<MFB_MODE_ATOMIC>
-                                  : (const void*)sgd_epoch_kernel_b4<MFB_MODE_HOGWILD>;
     const LaunchShape ls = pick_launch(c, k, LPR, a.nruns - a.run_begin, d->max_item_share, d->nruns,
-                                       b4 ? 8 : B, a.eta);
+                                       B, a.eta);
     void* args[] = {(void*)&a};
     MFB_CUDA(cudaLaunchKernel(k, dim3(ls.grid), dim3(ls.threads), args, 0, c->stream));
   }

@@ -171,6 +171,21 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
     int ri = -1, cur_end = span_lo, uid = -1, uid_before = -1;  // uid_before: user of the run before ri
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     float bu = 0.f;
+    float4 t0 = t;  // the row and bias as the current run found them
+    float bu0 = 0.f;
+    // write-back of a finished run.  ATOMIC: the user row receives what the run added to it as a reduction, so
+    // a second run of the same user in flight elsewhere (another split of the file, another DSGD piece, the
+    // other compute stream of a chunked epoch) loses nothing - its row is merely stale, like an item row
+    auto retire = [&]() {
+      if (MODE == MFB_MODE_ATOMIC) {
+        if (lane_ok)
+          burst_red4(theta4 + (int64_t)uid * nvec + lane, make_float4(t.x - t0.x, t.y - t0.y, t.z - t0.z, t.w - t0.w));
+        if (lane0) burst_red1(a.bu + uid, bu - bu0);
+      } else {
+        if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
+        if (lane0) __stcg(a.bu + uid, bu);
+      }
+    };
     int up_i[2], up_end[2], up_uid[2], up_iter[2];
     up_i[0] = next_run(-1, span_lo, &up_end[0], &up_uid[0]);
     up_i[1] = next_run(up_i[0], up_end[0], &up_end[1], &up_uid[1]);
@@ -237,8 +252,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       // ---- run switch: the batch about to be computed opens run up_i[0] ---------------------------
       if (qnew[0]) {
         if (ri >= 0) {
-          if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
-          if (lane0) __stcg(a.bu + uid, bu);
+          retire();
         }
         const int nuid = up_uid[0];
         if (nuid == uid) {
@@ -258,6 +272,8 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
         }
         uid_before = uid;
         uid = nuid;
+        t0 = t;  // what the run starts from (a continued user: what was just written back)
+        bu0 = bu;
         ri = up_i[0];
         cur_end = up_end[0];
         up_i[0] = up_i[1];
@@ -366,8 +382,7 @@ __global__ void __launch_bounds__(128) sgd_burst_kernel(const SgdArgs a, const i
       sc = sc == S - 1 ? 0 : sc + 1;
     }
     // last run of the span
-    if (lane_ok) __stcg(theta4 + (int64_t)uid * nvec + lane, t);
-    if (lane0) __stcg(a.bu + uid, bu);
+    retire();
     cp_async_wait<0>();  // nothing of this span may land in the buffers of the next one
     __syncwarp();
   }

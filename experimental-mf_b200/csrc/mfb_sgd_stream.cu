@@ -91,7 +91,8 @@ struct StreamSmem {
   static constexpr int BIAS_BYTES = R * SUBS * 16;
   static constexpr int CHUNK_BYTES = 2 * 32 * 8;        // [2][vid 32 x int | rating 32 x float]
   static constexpr int PFT_BYTES = 32 * VPL * 16;
-  static constexpr int WARP_BYTES = RING_BYTES + BIAS_BYTES + CHUNK_BYTES + PFT_BYTES;
+  static constexpr int T0_BYTES = 32 * VPL * 16;        // the factor row as the run found it (ATOMIC: delta write-back)
+  static constexpr int WARP_BYTES = RING_BYTES + BIAS_BYTES + CHUNK_BYTES + PFT_BYTES + T0_BYTES;
 };
 
 }  // namespace
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
   const uint32_t bias_sub = wbase + SM::RING_BYTES + sub * 16;    // + s*SUBS*16
   const uint32_t chunk0 = wbase + SM::RING_BYTES + SM::BIAS_BYTES;  // + buf*256 (+128 for ratings)
   const uint32_t pft_me = chunk0 + SM::CHUNK_BYTES + (sub * SM::ROW_F4 + gl) * 16;
+  const uint32_t t0_me = pft_me + SM::PFT_BYTES;  // written and read by this lane only: no barrier needed
   {  // zero everything once: vectors a lane never copies (ok[i] false) must read as zeros
     float4* w = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * SM::WARP_BYTES);
     for (int q = lane; q < SM::WARP_BYTES / 16; q += 32) w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
   int cbase = 0, cbuf = 0;           // records [cbase, cbase+LPR) are in chunk buffer cbuf
   int step = 0;                      // steps executed (= cp.async groups committed in the main loop)
   float4 t[VPL];
-  float bu = 0.f, pf_bu = 0.f;
+  float bu = 0.f, pf_bu = 0.f, bu0 = 0.f;
   float fr[R];
   int fv[R];
   int fver[R];                       // probe: version of the item when its row was gathered
@@ -244,10 +246,24 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
       // ---- run switch / span end (divergent, once per user-run) -------------------------------
       if (act && jc == cur_end) {
         if (ri >= 0) {  // retire the finished run
+          if (MODE == MFB_MODE_ATOMIC) {
+            // the user row receives what this run added to it, as a reduction: a second run of the same
+            // user that is in flight elsewhere (another split of the file, the other compute stream of a
+            // chunked epoch, a neighbouring span) then loses nothing - its row is merely stale, like an
+            // item row (the reference's in-place Hogwild loses single stores at most, mf.h:103-107)
 #pragma unroll
-          for (int i = 0; i < VPL; i++)
-            if (ok[i]) __stcg(theta4 + (int64_t)uid * a.nvec + gl + i * LPR, t[i]);
-          if (gl == 0) __stcg(a.bu + uid, bu);
+            for (int i = 0; i < VPL; i++) {
+              const float4 t0 = lds4(t0_me + i * LPR * 16);
+              red_add4p(theta4 + (int64_t)uid * a.nvec + gl + i * LPR,
+                        make_float4(t[i].x - t0.x, t[i].y - t0.y, t[i].z - t0.z, t[i].w - t0.w), ok[i]);
+            }
+            if (gl == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a.bu + uid), "f"(bu - bu0) : "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < VPL; i++)
+              if (ok[i]) __stcg(theta4 + (int64_t)uid * a.nvec + gl + i * LPR, t[i]);
+            if (gl == 0) __stcg(a.bu + uid, bu);
+          }
         }
         if (jc == span_hi) {
           act = false;  // a new span is claimed at the top of the outer loop
@@ -276,6 +292,13 @@ __global__ void __launch_bounds__(128) sgd_stream_kernel(const SgdArgs a, const 
             bu = __ldcg(a.bu + nuid);
           }
           uid = nuid;
+          if (MODE == MFB_MODE_ATOMIC) {  // what the run starts from (a continued user: what was just sent)
+#pragma unroll
+            for (int i = 0; i < VPL; i++)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(t0_me + i * LPR * 16), "f"(t[i].x), "f"(t[i].y),
+                           "f"(t[i].z), "f"(t[i].w) : "memory");
+            bu0 = bu;
+          }
           // fetch the next run's factor row now; it is needed one whole run from here
           pf_ri = ri + 1;
           if (pf_ri < span_n) {

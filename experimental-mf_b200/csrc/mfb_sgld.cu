@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
     Row<VPL> t = load_row<LPR, VPL>(a.theta, uid, a.nvec, gl);
     float bu = (gl == 0) ? __ldcg(a.bu + uid) : 0.f;
     bu = __shfl_sync(m, bu, 0, LPR);
+    const Row<VPL> t_in = t;
+    const float bu_in = bu;
     const float ur = __ldg(a.ur + uid);
     const float au = -a.eta * ur * a.bound;                                       // dpmf.h:78
     const double cbu = 1.0 - (double)(a.eta * a.lambda_ub * ur * a.bound);        // dpmf.h:84
@@ -310,8 +312,20 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
       }
       uc = 1;  // consecutive records of a run are consecutive clock ticks
     }
-    store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
-    if (gl == 0) __stcg(a.bu + uid, bu);
+    if (ORDERED) {
+      store_row<LPR, VPL>(a.theta, uid, a.nvec, gl, t);
+      if (gl == 0) __stcg(a.bu + uid, bu);
+    } else {
+      // the user row, too, receives its increment (noise + drift) as a reduction: a second run of the same
+      // user in flight in another group loses neither its gradient steps nor - the variance invariant - its noise
+      Row<VPL> dt;
+#pragma unroll
+      for (int i = 0; i < VPL; i++)
+        dt.v[i] = make_float4(t.v[i].x - t_in.v[i].x, t.v[i].y - t_in.v[i].y, t.v[i].z - t_in.v[i].z,
+                              t.v[i].w - t_in.v[i].w);
+      red_add_row<LPR, VPL>(a.theta, uid, a.nvec, gl, dt);
+      if (gl == 0) atomicAdd(a.bu + uid, bu - bu_in);
+    }
   }
 }
 

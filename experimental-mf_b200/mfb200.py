@@ -60,6 +60,8 @@ SIGNATURES = {
     "mfb_generate": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                C.POINTER(C.c_void_p)]),
     "mfb_sgd_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "mfb_sgd_epoch_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "mfb_dataset_num_blocks": (C.c_int64, [C.c_void_p, C.c_int]),
     "mfb_sgd_epoch_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float,
                                           C.c_float, C.c_int, C.c_int64]),
     "mfb_dataset_refresh_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -86,6 +88,8 @@ SIGNATURES = {
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
     "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "mfb_dsgd_epoch_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                    C.c_float, C.c_int]),
     "mfb_dsgd_timeline": (C.c_int, [C.c_void_p, f32p, C.c_int]),
     "mfb_placement_report": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]),
     "mfb_comm_allgather_items": (C.c_int, [C.c_void_p, i32p]),
@@ -376,6 +380,12 @@ class Context:
     def sgd_epoch(self, ds, eta, lam, gb, mode=MODE_HOGWILD):
         _check(lib().mfb_sgd_epoch(self.h, ds, eta, lam, gb, mode))
 
+    def sgd_epoch_blocks(self, ds, block_begin, block_end, eta, lam, gb, mode=MODE_ATOMIC):
+        _check(lib().mfb_sgd_epoch_blocks(self.h, ds, block_begin, block_end, eta, lam, gb, mode))
+
+    def num_blocks(self, ds):
+        return lib().mfb_dataset_num_blocks(self.h, ds)
+
     def dataset_refresh_from_host(self, ds, blocks):
         _check(lib().mfb_dataset_refresh_from_host(self.h, ds, blocks.h))
 
@@ -433,10 +443,10 @@ class Context:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _check(lib().mfb_comm_init(self.h, rank, world, buf))
 
-    def dsgd_epoch(self, datasets, item_bounds, eta, lam, gb, mode=MODE_ATOMIC):
+    def dsgd_epoch(self, datasets, item_bounds, eta, lam, gb, mode=MODE_ATOMIC, halves=1, rotations=1):
         ds = (C.c_int * len(datasets))(*datasets)
         b = np.ascontiguousarray(item_bounds, np.int32)
-        _check(lib().mfb_dsgd_epoch(self.h, ds, b.ctypes.data_as(i32p), eta, lam, gb, mode))
+        _check(lib().mfb_dsgd_epoch_ex(self.h, ds, b.ctypes.data_as(i32p), halves, rotations, eta, lam, gb, mode))
 
     def placement_report(self, which=None):
         """(calibration ms of every candidate placement, index of the one kept) for the plane-layout
@@ -448,8 +458,9 @@ class Context:
         n = lib().mfb_placement_report(self.h, which, ms.ctypes.data_as(f32p), 64, C.byref(best))
         return ms[:max(n, 0)].tolist(), best.value
 
-    def dsgd_timeline(self, world):
-        out = np.zeros(2 * world, np.float32)
+    def dsgd_timeline(self, steps):
+        """(wait ms, kernel ms) alternating, for the first `steps` cell kernels of the most recent DSGD epoch"""
+        out = np.zeros(2 * steps, np.float32)
         n = lib().mfb_dsgd_timeline(self.h, out.ctypes.data_as(f32p), len(out))
         if n < 0:
             _check(n)
@@ -496,6 +507,18 @@ class Context:
         out = (C.c_int * 4)()
         _check(lib().mfb_last_launch(self.h, out))
         return {"kernel": out[0], "grid": out[1], "threads": out[2], "ring": out[3]}
+
+
+def seeded_model(nu, nv, dim, seed, scale=1e-2):
+    """(theta[nu][dim], phi[nv][dim], bu[nu], bv[nv]) ~ N(0,1)*scale from numpy's seeded generator: the initial
+    model of every full-size parity run (tests/golden/make_fullsize_golden.py feeds the same arrays to the
+    reference, whose own init is clock-seeded, model.cc:3-5); equals tests/oraclelib.Model(nu, nv, dim, seed)."""
+    rng = np.random.default_rng(seed)
+    theta = rng.standard_normal((nu, dim), dtype=np.float32) * np.float32(scale)
+    phi = rng.standard_normal((nv, dim), dtype=np.float32) * np.float32(scale)
+    bu = rng.standard_normal(nu, dtype=np.float32) * np.float32(scale)
+    bv = rng.standard_normal(nv, dtype=np.float32) * np.float32(scale)
+    return theta, phi, bu, bv
 
 
 def comm_unique_id():

@@ -29,12 +29,26 @@ def dsgd_schedule(rank, world):
     return [((rank + s) % world, (rank - 1) % world, (rank + 1) % world) for s in range(world)]
 
 
+FIRST_EPOCH_ROTATIONS = 16  # turns of the ring in epoch 1 (DESIGN.md 5, tools/dsgd_order_study.py)
+HALVES = 2                  # pieces per item block: the shift of one travels while the other is computed
+
+
+def piece_schedule(rank, world, halves=1, rotations=1):
+    """[(turn, cell index = block * halves + piece)] in launch order for one epoch of rank `rank`."""
+    return [(r, ((rank + s) % world) * halves + h) for r in range(rotations) for s in range(world) for h in range(halves)]
+
+
 class DsgdWorker:
     """This rank's shard of the model and data on its GPU, plus the NCCL ring."""
 
-    def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200, merge=False):
+    def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200, merge=False,
+                 halves=None, first_epoch_rotations=None):
         self.rank, self.world, self.nv = rank, world, nv
-        self.bounds = item_bounds(nv, world)
+        self.halves = (HALVES if halves is None else halves) if world > 1 else 1
+        self.first_epoch_rotations = (FIRST_EPOCH_ROTATIONS if first_epoch_rotations is None else first_epoch_rotations) \
+            if world > 1 else 1
+        self.bounds = item_bounds(nv, world * self.halves)   # pieces
+        self.home_bounds = self.bounds[::self.halves]        # blocks (one per rank)
         self.ctx = mb.Context(nu, nv, k, device)
         self.ctx.init_normal(seed, 1e-2)  # counter-based: identical on every rank
         self.cells = train.split_by_item(self.bounds)
@@ -51,10 +65,17 @@ class DsgdWorker:
         self.test_ds = self.ctx.dataset_from_blocks(test)
         self.ntrain = sum(b.nratings for b in self.cells)
         self.ntest = test.nratings
+        self.epochs_done = 0
         self.ctx.comm_init(rank, world, unique_id)
 
-    def epoch(self, eta, lam, gb, mode=mb.MODE_ATOMIC):
-        self.ctx.dsgd_epoch(self.cell_ds, self.bounds, eta, lam, gb, mode)
+    def epoch(self, eta, lam, gb, mode=mb.MODE_ATOMIC, rotations=None):
+        if rotations is None:
+            rotations = self.first_epoch_rotations if self.epochs_done == 0 else 1
+        nb = min(self.ctx.num_blocks(ds) for ds in self.cell_ds)
+        rotations = max(1, min(rotations, nb))
+        self.ctx.dsgd_epoch(self.cell_ds, self.bounds, eta, lam, gb, mode, self.halves, rotations)
+        self.epochs_done += 1
+        return rotations
 
     def refresh_from_host(self):
         for ds, b in zip(self.cell_ds, self.cells):
@@ -62,7 +83,7 @@ class DsgdWorker:
 
     def global_sse(self, gb):
         """test SSE over all ranks; needs every item block, so the home blocks are gathered first"""
-        self.ctx.allgather_items(self.bounds)
+        self.ctx.allgather_items(self.home_bounds)
         s, n = self.ctx.sse(self.test_ds, gb)
         return self.ctx.allreduce_sse(s, n)
 

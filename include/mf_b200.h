@@ -162,6 +162,11 @@ int mfb_generate(const mfb_gen_params* p, mfb_blocks** train, mfb_blocks** test,
  * SgdFilter::operator() over every block of the file (mf.h:76-132): one SGD epoch with
  * learning rate eta, regulariser lambda, global bias gb. */
 int mfb_sgd_epoch(mfb_ctx* ctx, int ds, float eta, float lambda, float gb, int mode);
+/* SgdFilter::operator() over Blocks [block_begin, block_end) of the file only (the reference calls the
+ * filter once per Block, mf.h:76): a slice of an epoch.  Used by hosts that interleave several files. */
+int mfb_sgd_epoch_blocks(mfb_ctx* ctx, int ds, int64_t block_begin, int64_t block_end, float eta, float lambda,
+                         float gb, int mode);
+int64_t mfb_dataset_num_blocks(mfb_ctx* ctx, int ds);
 /* The same epoch with the rating tiles starting in HOST memory (the reference re-reads its
  * training file every epoch, mf.h:24-45): the arrays of `src` (pin them once with
  * mfb_blocks_pin) are copied H2D in chunks of about `chunk_ratings` records (0 = default) on a
@@ -240,9 +245,18 @@ int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
 int mfb_comm_destroy(mfb_ctx* ctx);
 int mfb_dsgd_epoch(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
                    float gb, int mode);
-/* diagnostic: the most recent mfb_dsgd_epoch on this rank as out[2s] = ms of the cell kernel of sub-epoch
- * s, out[2s+1] = ms the compute stream then waited for the ring shift; returns the number of entries
- * written (<= n) or a negative error */
+/* The general form.  halves = H >= 1: every rank's item block is cut into H pieces (item_bounds has world*H+1
+ * entries, datasets world*H cells, block of rank r = pieces r*H .. r*H+H-1); the shift of piece h travels on the
+ * communication stream while the kernel on piece h+1 runs, so the exchange and the ring neighbour's lag are hidden
+ * behind compute (H = 2: the overlap SURVEY.md 8e asks for).  rotations = R >= 1: the ring turns R times in the
+ * epoch, turn r over the r-th of R runs of consecutive Blocks of every cell.  R > 1 in the FIRST epoch keeps the
+ * multi-GPU test RMSE on the single-GPU trajectory; later epochs use R = 1.
+ * mfb_dsgd_epoch == halves 1, rotations 1. */
+int mfb_dsgd_epoch_ex(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, int halves, int rotations,
+                      float eta, float lambda, float gb, int mode);
+/* diagnostic: the most recent DSGD epoch on this rank, kernel by kernel in launch order: out[2i] = ms the compute
+ * stream waited before kernel i for its item rows (ring shift issued one sub-epoch earlier), out[2i+1] = ms of
+ * kernel i; returns the number of entries written (<= n) or a negative error */
 int mfb_dsgd_timeline(mfb_ctx* ctx, float* out, int n);
 /* make all of phi/bv valid on every rank (each rank publishes its home block) - before evaluation */
 int mfb_comm_allgather_items(mfb_ctx* ctx, const int32_t* item_bounds);

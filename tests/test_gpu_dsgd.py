@@ -29,9 +29,9 @@ def test_world_size_one_ring_equals_plain_epoch():
         c.sgd_epoch(d, mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
     for a, b in zip(w.ctx.get_factors(), c.get_factors()):
         np.testing.assert_array_equal(a, b)
-    # the timeline diagnostic: one cell kernel, one (empty) shift slot, both non-negative, kernel > 0
+    # the timeline diagnostic: (wait for the item rows, kernel) of the one cell kernel
     tl = w.ctx.dsgd_timeline(1)
-    assert len(tl) == 2 and tl[0] > 0 and tl[1] >= 0
+    assert len(tl) == 2 and tl[0] >= 0 and tl[1] > 0
     s, n = w.global_sse(GB)
     s2, n2 = c.sse(c.dataset_from_blocks(te), GB)
     assert n == n2 and abs(s - s2) <= 1e-9 * s2

@@ -62,7 +62,7 @@ def test_ordered_sgd_matches_oracle_all_row_shapes(dim):
 
 
 # (kernel, ring depth | batch size + 10 * batches requested ahead)
-KERNELS = [(3, 1), (3, 2), (3, 4), (4, 14), (4, 24), (4, 18), (4, 28), (2, 0)]
+KERNELS = [(3, 1), (3, 2), (3, 4), (4, 14), (4, 24), (4, 18), (4, 28), (1, 0)]
 
 
 def pick_kernel(c, kernel, depth):
@@ -121,6 +121,53 @@ def test_parallel_modes_exact_on_ragged_runs_with_private_items(mode, dim, kerne
     c.sgd_epoch(d, 0.05, 0.02, GB, mode)
     oracle_sgd(m, ds, 0.05, 0.02, GB)
     assert model_rel_err(c, m) <= 2e-5
+    c.close()
+
+
+@pytest.mark.parametrize("kernel,depth", [(3, 4), (3, 1), (4, 14), (1, 0)])
+@pytest.mark.parametrize("dim", [32, 128])
+def test_concurrent_runs_of_one_user_lose_nothing(dim, kernel, depth):
+    """a file holds several runs per user (getdata --split, DSGD pieces, chunked epochs on two
+    streams) and two of them can be in flight in different groups at once.  The ATOMIC schedule sends the user
+    row's INCREMENT as a reduction, so both runs' contributions arrive.  Data: every user has two one-record
+    runs, N runs apart (different spans, claimed at the same moment at full machine width); the two items of
+    a user have disjoint supports (first / second half of the row) and lambda = 0, so run A only moves the
+    first half of theta_u, run B only the second half, and either one missing is visible exactly."""
+    N, half = 2048, dim // 2
+    rng = np.random.default_rng(dim)
+    m = ol.Model(N, 2 * N, dim, seed=9, scale=0.3)
+    m.phi[:N, half:] = 0.0          # items 0..N-1: support = first half
+    m.phi[N:, :half] = 0.0          # items N..2N-1: support = second half
+    m.bu[:] = 0.0
+    m.bv[:] = 0.0
+    theta0, phi0 = m.theta.copy(), m.phi.copy()
+    uid = np.r_[np.arange(N), np.arange(N)].astype(np.int32)
+    vid = np.r_[np.arange(N), N + np.arange(N)].astype(np.int32)
+    r = rng.integers(1, 6, 2 * N).astype(np.float32)
+    ds = ol.Dataset(np.r_[np.arange(0, 2 * N, 500), 2 * N], uid, np.arange(2 * N + 1), vid, r)
+    c = ctx_from_model(m)
+    c.set_option("row_concurrency", 0)
+    c.set_option("run_fraction_ppm", 0)
+    pick_kernel(c, kernel, depth)
+    d = upload_ds(c, ds)
+    eta = 0.01
+    c.sgd_epoch(d, eta, 0.0, GB, mb.MODE_ATOMIC)
+    th, ph, bu, bv = c.get_factors()
+    dth = th.astype(np.float64) - theta0[:, :dim]
+    # what each run adds when it sees bu = 0; if it saw the other run's bu = e_other instead, its own e moves
+    # by eta * e_other <= 4e-4, i.e. by < 8 % for the records with |residual| >= 0.5 that are checked
+    ea = eta * (r[:N] - np.einsum("ij,ij->i", theta0[:, :dim], phi0[:N, :dim]) - GB)
+    eb = eta * (r[N:] - np.einsum("ij,ij->i", theta0[:, :dim], phi0[N:, :dim]) - GB)
+    want_a = ea[:, None] * phi0[:N, :half]
+    want_b = eb[:, None] * phi0[N:, half:dim]
+    na, nb = np.linalg.norm(want_a, axis=1), np.linalg.norm(want_b, axis=1)
+    err_a = np.linalg.norm(dth[:, :half] - want_a, axis=1) / na
+    err_b = np.linalg.norm(dth[:, half:] - want_b, axis=1) / nb
+    # a lost run would give a relative error of exactly 1 for that user and half
+    big_a, big_b = np.abs(ea) >= 0.5 * eta, np.abs(eb) >= 0.5 * eta
+    assert big_a.sum() > N // 4 and big_b.sum() > N // 4
+    assert err_a[big_a].max() < 0.2 and err_b[big_b].max() < 0.2, (err_a[big_a].max(), err_b[big_b].max())
+    assert np.abs(bu - (ea + eb)).max() < 1e-3
     c.close()
 
 
