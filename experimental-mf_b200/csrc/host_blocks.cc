@@ -121,47 +121,83 @@ int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bou
   return MFB_OK;
 }
 
-// One run per user: the user's runs concatenated in file order, users in the order of their first
-// run, `users_per_block` runs per Block.  (A DSGD cell holds, for each user, the pieces of `split`
-// runs of the source file; merging them restores the length of the user's burst of updates.)
-int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out) {
+// Regrouping of a file's runs (the order of updates is the caller's business: see DESIGN.md 5 - after the first
+// epoch it does not matter for the result, so the steady-state DSGD cells are regrouped for speed).
+//   merge_users: one run per user - the user's runs concatenated in file order, users in the order of their first
+//     run.  (A DSGD cell holds, for each user, the pieces of `split` runs of the source file; merged, the factor row
+//     is read and written once per cell instead of once per piece.)
+//   longest_first: runs in descending order of length (stable) - longest-processing-time-first scheduling: a launch
+//     ends when its longest run still in flight ends, and a run is a sequential chain.
+// `users_per_block` runs per Block.
+int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, int users_per_block, mfb_blocks** out) {
   MFB_REQUIRE(b && out && users_per_block >= 1, "bad argument");
   const Dataset& d = b->d;
   const int64_t nruns = (int64_t)d.h_run_uid.size();
-  int32_t maxu = -1;
-  for (int32_t u : d.h_run_uid) maxu = std::max(maxu, u);
-  std::vector<int64_t> count((size_t)maxu + 2, 0);
-  std::vector<int32_t> order;  // users by first appearance
-  for (int64_t r = 0; r < nruns; r++) {
-    const int32_t u = d.h_run_uid[r];
-    if (count[u] == 0 && d.h_run_off[r + 1] > d.h_run_off[r]) order.push_back(u);
-    count[u] += d.h_run_off[r + 1] - d.h_run_off[r];
+  // groups: the output runs, each a list of source runs in file order
+  std::vector<int64_t> group_of((size_t)nruns, -1);
+  std::vector<int32_t> g_uid;
+  std::vector<int64_t> g_len;
+  if (merge_users) {
+    int32_t maxu = -1;
+    for (int32_t u : d.h_run_uid) maxu = std::max(maxu, u);
+    std::vector<int64_t> g_of_user((size_t)maxu + 2, -1);
+    for (int64_t r = 0; r < nruns; r++) {
+      const int64_t len = d.h_run_off[r + 1] - d.h_run_off[r];
+      if (len == 0) continue;
+      const int32_t u = d.h_run_uid[r];
+      if (g_of_user[u] < 0) {
+        g_of_user[u] = (int64_t)g_uid.size();
+        g_uid.push_back(u);
+        g_len.push_back(0);
+      }
+      group_of[r] = g_of_user[u];
+      g_len[g_of_user[u]] += len;
+    }
+  } else {
+    for (int64_t r = 0; r < nruns; r++) {
+      const int64_t len = d.h_run_off[r + 1] - d.h_run_off[r];
+      if (len == 0) continue;
+      group_of[r] = (int64_t)g_uid.size();
+      g_uid.push_back(d.h_run_uid[r]);
+      g_len.push_back(len);
+    }
   }
-  std::vector<int64_t> slot((size_t)maxu + 2, -1), fill((size_t)maxu + 2, 0);
+  const int64_t ng = (int64_t)g_uid.size();
+  std::vector<int64_t> order((size_t)ng);
+  for (int64_t i = 0; i < ng; i++) order[i] = i;
+  if (longest_first)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return g_len[x] > g_len[y]; });
+  std::vector<int64_t> slot((size_t)ng), fill((size_t)ng, 0);
   mfb_blocks* o = blocks_new();  // run_off = block_off = {0}
   Dataset& m = o->d;
   int64_t total = 0;
-  for (size_t i = 0; i < order.size(); i++) {
-    const int32_t u = order[i];
-    slot[u] = total;
-    total += count[u];
-    m.h_run_uid.push_back(u);
+  for (int64_t i = 0; i < ng; i++) {
+    const int64_t g = order[i];
+    slot[g] = total;
+    total += g_len[g];
+    MFB_REQUIRE(total < (int64_t)INT32_MAX, "file too large for int32 offsets");
+    m.h_run_uid.push_back(g_uid[g]);
     m.h_run_off.push_back((int32_t)total);
-    if ((i + 1) % (size_t)users_per_block == 0) m.h_block_off.push_back((int64_t)m.h_run_uid.size());
+    if ((i + 1) % users_per_block == 0) m.h_block_off.push_back((int64_t)m.h_run_uid.size());
   }
   if (m.h_block_off.back() != (int64_t)m.h_run_uid.size()) m.h_block_off.push_back((int64_t)m.h_run_uid.size());
   m.h_vid.resize(total);
   m.h_rating.resize(total);
   for (int64_t r = 0; r < nruns; r++) {
-    const int32_t u = d.h_run_uid[r];
-    for (int32_t t = d.h_run_off[r]; t < d.h_run_off[r + 1]; t++) {
-      const int64_t at = slot[u] + fill[u]++;
-      m.h_vid[at] = d.h_vid[t];
-      m.h_rating[at] = d.h_rating[t];
-    }
+    const int64_t g = group_of[r];
+    if (g < 0) continue;
+    const int64_t n = d.h_run_off[r + 1] - d.h_run_off[r], at = slot[g] + fill[g];
+    memcpy(m.h_vid.data() + at, d.h_vid.data() + d.h_run_off[r], (size_t)n * sizeof(int32_t));
+    memcpy(m.h_rating.data() + at, d.h_rating.data() + d.h_run_off[r], (size_t)n * sizeof(float));
+    fill[g] += n;
   }
   *out = o;
   return MFB_OK;
+}
+
+// one run per user, users in order of first appearance
+int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out) {
+  return mfb_blocks_regroup(b, 1, 0, users_per_block, out);
 }
 
 void mfb_blocks_free(mfb_blocks* b) {

@@ -19,7 +19,7 @@ static void show_help() {  // main.cc:6-33: one line per flag, same names and me
       "--alg        [xxx]     : xxx can be {mf, dpmf, admf}.",
       "--dim        [int]     : low rank of the model.",
       "--iter       [int]     : number of iterations.",
-      "--fly        [int]     : number of updates in flight (1 = single-thread update order).",
+      "--fly        [int]     : 1 = single-thread update order; > 1 = parallel schedule (the GPU picks its width).",
       "--stride     [int]     : prefetch strides (accepted, unused on the GPU).",
       "--eta        [float]   : learning rate.",
       "--lambda     [float]   : regularizer.",
@@ -32,7 +32,7 @@ static void show_help() {  // main.cc:6-33: one line per flag, same names and me
       "--noise_size [int]     : the Gaussian numbers lookup table (accepted, unused: Philox stream).",
       "--eta_reg    [float]   : the learning rate for estimating regularization parameters.",
       "--loss       [int]     : the loss type can be {least square, 0-1 logistic regression}.",
-      "--measure    [int]     : support RMSE.",
+      "--measure    [int]     : 0 = RMSE as the reference computes it; 1 = RMSE after the link of --loss.",
   };
   printf("Usage:\n./mf\n");
   for (const char* l : lines) printf("%s\n", l);

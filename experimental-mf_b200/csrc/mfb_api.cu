@@ -73,7 +73,7 @@ static int64_t bounded_groups_alone(const Context* c, int64_t groups, double max
     const double budget = (double)c->opt_row_concurrency * widen;
     groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(budget / (max_item_share * std::max(inflight, 0.1)))));
   }
-  if (c->opt_run_fraction_ppm > 0 && total_runs > 0) {
+  if (c->opt_run_fraction_ppm > 0 && total_runs > 0 && c->model_age < c->opt_run_bound_epochs) {
     const double frac = (double)c->opt_run_fraction_ppm * 1e-6 * (c->opt_eta_scaling >= 2 ? widen : 1.0);
     groups = std::min<int64_t>(groups, std::max<int64_t>(1, (int64_t)(total_runs * frac)));
   }
@@ -468,6 +468,12 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
   } else if (!strcmp(name, "run_fraction_ppm")) {
     MFB_REQUIRE(value >= 0, "run_fraction_ppm must be >= 0");
     c->opt_run_fraction_ppm = value;
+  } else if (!strcmp(name, "run_bound_epochs")) {
+    MFB_REQUIRE(value >= 0, "run_bound_epochs must be >= 0");
+    c->opt_run_bound_epochs = value;
+  } else if (!strcmp(name, "model_age")) {
+    MFB_REQUIRE(value >= 0, "model_age must be >= 0");
+    c->model_age = value;
   } else if (!strcmp(name, "max_groups")) {
     MFB_REQUIRE(value >= 0, "max_groups must be >= 0");
     c->opt_max_groups = value;
@@ -559,6 +565,7 @@ static int xfer(mfb_ctx* h, int which, float* host, int64_t row0, int64_t nrows,
   if (nrows == 0) return MFB_OK;
   MFB_CUDA(cudaSetDevice(c->device));
   float* dev = c->arr[which] + row0 * ds;
+  if (up && (which == MFB_THETA || which == MFB_PHI)) c->model_age = 0;  // a new model: young until told otherwise
   if (up)
     MFB_CUDA(cudaMemcpy2DAsync(dev, ds * sizeof(float), host, hs * sizeof(float),
                                cols * sizeof(float), nrows, cudaMemcpyHostToDevice, c->stream));
@@ -579,6 +586,7 @@ int mfb_download(mfb_ctx* h, int which, float* host, int64_t row0, int64_t nrows
 int mfb_init_normal(mfb_ctx* h, uint64_t seed, float scale) {
   MFB_REQUIRE(h, "ctx is NULL");
   MFB_CUDA(cudaSetDevice(h->c.device));
+  h->c.model_age = 0;
   return launch_fill_normal(&h->c, seed, scale);
 }
 
@@ -785,6 +793,7 @@ int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mod
   }
   c->planes_allowed = false;
   end_timing(c);
+  if (rc == MFB_OK) c->model_age++;
   return rc;
 }
 
@@ -935,6 +944,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_CUDA(cudaEventRecord(c->ev_s2, c->stream2));
   MFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_s2, 0));
   end_timing(c);
+  c->model_age++;
   return MFB_OK;
 }
 
@@ -1043,8 +1053,11 @@ int mfb_blocks_unpin(mfb_blocks* b) {
   return MFB_OK;
 }
 
-int mfb_sse(mfb_ctx* h, int ds, float gb, double* sse, int64_t* n) {
+int mfb_sse(mfb_ctx* h, int ds, float gb, double* sse, int64_t* n) { return mfb_sse_link(h, ds, gb, 0, sse, n); }
+
+int mfb_sse_link(mfb_ctx* h, int ds, float gb, int link, double* sse, int64_t* n) {
   MFB_REQUIRE(h && sse, "NULL argument");
+  MFB_REQUIRE(link == 0 || link == 1, "link must be 0 (identity) or 1 (logistic)");
   Context* c = &h->c;
   Dataset* d = get_ds(c, ds);
   if (!d) return MFB_E_ARG;
@@ -1054,7 +1067,7 @@ int mfb_sse(mfb_ctx* h, int ds, float gb, double* sse, int64_t* n) {
   if (n) *n = d->nratings;
   if (d->nruns == 0) return MFB_OK;
   begin_timing(c);
-  int rc = launch_sse(c, d, gb);
+  int rc = launch_sse(c, d, gb, link);
   end_timing(c);
   if (rc) return rc;
   MFB_CUDA(cudaMemcpyAsync(c->h_accum, c->d_accum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1115,6 +1128,7 @@ int mfb_sgld_epoch(mfb_ctx* h, int ds, const mfb_sgld_params* p, float gb, int m
   begin_timing(c);
   rc = d->nruns ? launch_sgld(c, d, p, gb, mode) : MFB_OK;
   end_timing(c);
+  if (rc == MFB_OK) c->model_age++;
   return rc;
 }
 
@@ -1254,6 +1268,7 @@ int mfb_admf_epoch(mfb_ctx* h, int ds, float eta, float eta_reg, int loss, float
   begin_timing(c);
   int rc = d->nruns ? launch_admf(c, d, eta, eta_reg, loss, gb, mode) : MFB_OK;
   end_timing(c);
+  if (rc == MFB_OK) c->model_age++;
   return rc;
 }
 

@@ -235,6 +235,7 @@ int mfb_dsgd_epoch_ex(mfb_ctx* h, const int* datasets, const int32_t* item_bound
     if (int rc = wait_shift(c, m, hh)) return rc;
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;
+  c->model_age++;
   return MFB_OK;
 }
 

@@ -154,6 +154,12 @@ struct Context {
                                 // one gains nothing per run (251 warp instructions per step bound it) and costs width
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
+  // ... which applies while the model is YOUNG: the order effect of interleaved runs is created in the first epoch,
+  // while the factors leave their random initialisation (tools/order_study.py: 5.6 % of the runs interleaved in
+  // every epoch: final tRMSE +1.7e-3; in every epoch but the first: +1e-4).  model_age counts the whole epochs
+  // applied since the factors were last set (init / upload); hosts that drive slices or load a trained model set it.
+  int model_age = 0;
+  int opt_run_bound_epochs = 1;
   std::vector<Dataset> datasets;
 };
 
@@ -192,7 +198,7 @@ int tune_placement(Context* c, Dataset* const* ds, int nds, float gb, int mode, 
 // runs [run_begin, run_end) of the dataset, in the given schedule
 int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mode,
                int64_t run_begin, int64_t run_end);
-int launch_sse(Context* c, Dataset* d, float gb);
+int launch_sse(Context* c, Dataset* d, float gb, int link = 0);
 int launch_fill_normal(Context* c, uint64_t seed, float scale);
 // expand n packed records (u16 item id, u8 rating code) into the SoA tiles
 int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* code, const float* dict, int32_t* vid,

@@ -189,6 +189,7 @@ struct SseArgs {
   double* accum;  // [0] += sum of squared errors
   int nruns, nvec;
   float gb;
+  int link;  // 0 identity (MF::calc_mse as written), 1 logistic (util.h:90-95)
 };
 
 template <int LPR, int VPL>
@@ -219,7 +220,10 @@ __global__ void __launch_bounds__(256) sse_kernel(const SseArgs a) {
         const float r = __shfl_sync(m, myr, b, LPR);
         const Row<VPL> f = load_row<LPR, VPL>(a.phi, v, a.nvec, gl);
         const float d = group_dot<LPR, VPL>(t, f, m);
-        const float err = r - d - bu - __ldcg(a.bv + v) - a.gb;  // model.cc:62-63
+        // model.cc:62-63; link = 1: the prediction goes through the logistic link first, as in the update and in
+        // updateReg (util.h:90-95 active(), admf.h:69, model.h:87) - the evaluation that matches --loss 1
+        const float bvv = __ldcg(a.bv + v);
+        const float err = a.link == 1 ? r - 1.0f / (1.0f + expf(-(d + bu + bvv + a.gb))) : r - d - bu - bvv - a.gb;
         if (gl == 0) acc += (double)(err * err);                 // model.cc:64
       }
     }
@@ -373,7 +377,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
     if (mode != MFB_MODE_ORDERED && nvec <= 32) {
       const int64_t runs = a.nruns - a.run_begin;
       const int64_t cap = (int64_t)c->sm_count * 64;  // more than either kernel holds: bounds only
-      const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 0.6, eta), runs);
+      const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 1.0, eta), runs);
       const double w_burst = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 8.0, eta), (runs + 31) / 32);
       const double stream = std::min(w_stream * c->rate_stream, 6.5e9), burst = std::min(w_burst * c->rate_burst, 5.8e9);
       if (burst > stream) c->use_kernel = 4;
@@ -396,7 +400,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
   return MFB_OK;
 }
 
-int launch_sse(Context* c, Dataset* d, float gb) {
+int launch_sse(Context* c, Dataset* d, float gb, int link) {
   SseArgs a;
   a.theta = c->arr[MFB_THETA];
   a.phi = c->arr[MFB_PHI];
@@ -410,6 +414,7 @@ int launch_sse(Context* c, Dataset* d, float gb) {
   a.nruns = (int)d->nruns;
   a.nvec = c->stride / 4;
   a.gb = gb;
+  a.link = link;
   MFB_CUDA(cudaMemsetAsync(c->d_accum, 0, sizeof(double), c->stream));
 #define CALL(L, V) return launch_sse_t<L, V>(c, a)
   MFB_DISPATCH_SHAPE(a.nvec, CALL);

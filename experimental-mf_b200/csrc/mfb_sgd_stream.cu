@@ -422,12 +422,17 @@ namespace {
 // at once, each applied with step eta: the product eta*inflight*p is what must stay bounded
 // (measured: divergence between 1.3 and 1.8 at eta = 0.02).  row_concurrency is that
 // bound expressed as a count at the reference's default eta = 0.02 (main.cc:97).
+// (Full Netflix shape, epoch 1, round 2: 6,720 sub-warps with R = 1 - 24 stale updates of the hottest row by the
+// probe's 0.75 rows per sub-warp, eta*c = 0.47 - is stable; 11,348 - eta*c = 0.8 - ends in NaN.  A sub-warp with
+// R = 1 therefore counts for one whole row: row_concurrency = 32 then means eta*c <= 0.48 measured.)
 template <int R>
-constexpr double ring_weight() { return R == 1 ? 0.6 : (double)R; }
+constexpr double ring_weight() { return (double)R; }
 
 template <int LPR, int VPL, int R>
 int64_t stream_capacity(Context* c, const void* k) {
   int per_sm = 0;
+  if (4 * StreamSmem<LPR, VPL, R>::WARP_BYTES > 48 * 1024)  // k = 128 with the deepest ring: 51 KB per CTA of 4 warps
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * StreamSmem<LPR, VPL, R>::WARP_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 4 * StreamSmem<LPR, VPL, R>::WARP_BYTES);
   per_sm = std::max(per_sm, 1);
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
@@ -449,6 +454,7 @@ int launch_stream_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   const int nruns = a.nruns - a.run_begin;
   const int subs_per_warp = 32 / LPR;
   constexpr int WARP_BYTES = StreamSmem<LPR, VPL, R>::WARP_BYTES;
+  if (4 * WARP_BYTES > 48 * 1024) MFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * WARP_BYTES));
   int64_t subs = std::min<int64_t>(stream_capacity<LPR, VPL, R>(c, k), std::max((nruns + LPR - 1) / LPR, 1));
   subs = bounded_groups(c, subs, d->max_item_share, d->nruns, ring_weight<R>(), a.eta);
   SgdArgs aa = a;

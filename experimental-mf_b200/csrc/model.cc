@@ -46,7 +46,7 @@ MF::MF(char* train_data, char* test_data, char* result, char* model, int dim, in
     : theta_(nullptr), phi_(nullptr), bu_(nullptr), bv_(nullptr), train_data_(train_data),
       test_data_(test_data), result_(result), model_(model), gb_(gb), dim_(dim), iter_(iter),
       eta_(eta), gam_(gam), lambda_(lambda), eta0_(eta), nu_(nu), nv_(nv), data_in_fly_(fly),
-      prefetch_stride_(stride), ctx_(nullptr), train_ds_(-1), device_(0) {
+      prefetch_stride_(stride), ctx_(nullptr), start_round_(0), train_ds_(-1), device_(0) {
   const char* dev = getenv("MF_DEVICE");
   if (dev) device_ = atoi(dev);
 }
@@ -71,9 +71,17 @@ void MF::alloc_host(int extra_floats) {
   phi_ = theta_ + nu_;
 }
 
+// `--fly N > 1` = the production schedule at the library's own width (model.h); an explicit hot-row budget
+// comes from the environment
+void MF::apply_options() {
+  const char* rc = getenv("MF_ROW_CONCURRENCY");
+  if (rc) check(mfb_set_option(ctx_, "row_concurrency", atoi(rc)), "row_concurrency");
+  if (start_round_ > 0) check(mfb_set_option(ctx_, "model_age", start_round_), "model_age");
+}
+
 void MF::init() {  // model.cc:10-34
   check(mfb_create(&ctx_, device_, nu_, nv_, dim_), "mfb_create");
-  if (data_in_fly_ > 1) check(mfb_set_option(ctx_, "row_concurrency", data_in_fly_), "row_concurrency");
+  apply_options();
   alloc_host(0);
   check(mfb_init_normal(ctx_, default_seed(), 1e-2f), "mfb_init_normal");  // N(0,1)*1e-2
   pull();
@@ -163,6 +171,35 @@ static void read_header(FILE* fp, const char* path, MF* m) {
   }
 }
 
+// the reference's checkpoint carries neither the round nor the step size, so a reloaded model
+// starts over at eta0.  A small text file next to the checkpoint keeps them; absent (a checkpoint written by the
+// reference), the run starts at round 1 as the reference would.
+void MF::write_state(const char* file, int round) const {
+  char path[600];
+  snprintf(path, sizeof path, "%s.state", file);
+  FILE* fp = fopen(path, "w");
+  if (!fp) die_io("create", path);
+  fprintf(fp, "mf_b200_state 1\nround %d\neta0 %.9g\ngam %.9g\neta %.9g\n", round, eta0_, gam_, eta_);
+  fclose(fp);
+}
+bool MF::read_state(const char* file) {
+  char path[600];
+  snprintf(path, sizeof path, "%s.state", file);
+  FILE* fp = fopen(path, "r");
+  if (!fp) return false;
+  int version = 0, round = 0;
+  float eta0 = 0.f, gam = 0.f, eta = 0.f;
+  const int got = fscanf(fp, "mf_b200_state %d round %d eta0 %g gam %g eta %g", &version, &round, &eta0, &gam, &eta);
+  fclose(fp);
+  if (got != 5 || version != 1 || round < 0) {
+    fprintf(stderr, "mf_b200: %s is not a state file of this program\n", path);
+    exit(3);
+  }
+  start_round_ = round;  // eta0 and gam stay the command line's: the next round uses eta0 / (round+1)^gam
+  if (ctx_) check(mfb_set_option(ctx_, "model_age", start_round_), "model_age");
+  return true;
+}
+
 void MF::read_model() {  // model.cc:75-97
   FILE* fp = fopen(model_, "rb");
   if (!fp) die_io("open", model_);
@@ -171,6 +208,7 @@ void MF::read_model() {  // model.cc:75-97
   read_factors(fp, model_, this);
   fclose(fp);
   push();
+  read_state(model_);  // (after push: an upload marks the model as new)
 }
 
 void MF::save_model(int round) {  // model.cc:98-122
@@ -185,6 +223,7 @@ void MF::save_model(int round) {  // model.cc:98-122
   fwrite(&lambda_, 4, 1, fp);
   write_factors(fp, this);
   fclose(fp);
+  write_state(file, round);
 }
 
 // ---------------------------------------------------------------------------------------- DPMF
@@ -202,7 +241,7 @@ DPMF::~DPMF() {}
 
 void DPMF::init() {  // model.cc:197-245
   check(mfb_create(&ctx_, device_, nu_, nv_, dim_), "mfb_create");
-  if (data_in_fly_ > 1) check(mfb_set_option(ctx_, "row_concurrency", data_in_fly_), "row_concurrency");
+  apply_options();
   check(mfb_enable(ctx_, 2), "mfb_enable(dpmf)");
   alloc_host(nu_ + nv_ + 2 * dim_);  // bu|bv|ur|vr|lambda_u|lambda_v, model.cc:199-204
   ur_ = bv_ + nv_;
@@ -344,6 +383,7 @@ void DPMF::save_model(int round) {
   fwrite(lambda_v_, sizeof(float), dim_, fp);
   write_factors(fp, this);
   fclose(fp);
+  write_state(file, round);
 }
 
 void DPMF::read_hyper() {  // model.cc:153-167
@@ -370,6 +410,7 @@ void DPMF::read_model() {  // model.cc:169-195
   read_factors(fp, model_, this);
   fclose(fp);
   push();
+  if (read_state(model_)) round_ = start_round_ + 1;
 }
 
 // ---------------------------------------------------------------------------------- AdaptRegMF
@@ -420,6 +461,14 @@ void AdaptRegMF::plain_read_valid(const char* valid) {  // model.cc:390-415
   check(mfb_admf_set_validation(ctx_, (int64_t)recsv_.size(), u.data(), v.data(), r.data()), "mfb_admf_set_validation");
 }
 
+float AdaptRegMF::calc_measure(const mf::Blocks& blocks, int& ndata) {
+  double sse = 0.0;
+  int64_t n = 0;
+  check(mfb_sse_link(ctx_, dataset_of(blocks), gb_, (measure_ == 1 && loss_ == 1) ? 1 : 0, &sse, &n), "mfb_sse_link");
+  ndata = (int)n;
+  return (float)sse;
+}
+
 void AdaptRegMF::admf_epoch() {
   const int64_t nruns = mfb_dataset_num_runs(ctx_, train_ds_);
   std::vector<int32_t> draws((size_t)nruns);
@@ -458,7 +507,7 @@ void run(MF& mf) {
   mf.load_train();
   lap("training file (parse, ingest)");
   s = Time::now();
-  for (int iter = 1; iter <= mf.iter_; iter++) {
+  for (int iter = mf.start_round_ + 1; iter <= mf.iter_; iter++) {  // (a model loaded with its .state continues)
     if (iter > 1) mf.seteta(iter);  // mf.h:38
     mf.sgd_epoch();
     check(mfb_sync(mf.ctx_), "mfb_sync");
@@ -474,14 +523,30 @@ void run(MF& mf) {
 
 void run(DPMF& dpmf) {  // main.cc:55-74
   dpmf.init();
-  if (dpmf.model_ != NULL) dpmf.read_hyper();
+  if (dpmf.model_ != NULL) {
+    // main.cc:57 loads the hyper-parameters only; a checkpoint that has its .state sidecar (written by
+    // DPMF::save_model here) is a resume point: factors, hyper-parameters, round and step size continue
+    char st[600];
+    snprintf(st, sizeof st, "%s.state", dpmf.model_);
+    FILE* f = fopen(st, "r");
+    if (f) {
+      fclose(f);
+      dpmf.read_model();
+      dpmf.seteta_cutoff(dpmf.start_round_ + 1);
+    } else {
+      dpmf.read_hyper();
+    }
+  }
   mf::Blocks blocks_test;
   plain_read(dpmf.test_data_, blocks_test);
   s = Time::now();
-  for (int i = 1; i <= dpmf.iter_; i++) {
+  for (int i = dpmf.start_round_ + 1; i <= dpmf.iter_; i++) {
     dpmf.sgld_epoch();
     dpmf.finish_round(blocks_test, i);
     fflush(stdout);
+    if (dpmf.result_ != NULL && getenv("MF_SAVE_EVERY") && i % atoi(getenv("MF_SAVE_EVERY")) == 0 &&
+        !(i >= 100 && i % 20 == 0))  // (finish_round saved that one already, model.cc:309)
+      dpmf.save_model(i);
   }
 }
 
@@ -500,7 +565,7 @@ void run(AdaptRegMF& admf) {  // main.cc:77-93 + AdRegReadFilter (admf.h:29-37)
     admf.admf_epoch();
     e = Time::now();
     int nn;
-    const float sse = admf.calc_mse(blocks_test, nn);
+    const float sse = admf.calc_measure(blocks_test, nn);  // --measure 0: MF::calc_mse, as admf.h:32 calls it
     printf("iter#%d\t%f\ttRMSE=%f\n", iter, std::chrono::duration<float>(e - s).count(), sqrt(sse * 1.0 / nn));  // admf.h:32
     if (getenv("MF_PRINT_LAMBDA"))  // the reference never prints them; opt-in extra line
       printf("lambda#%d\t%g\t%g\t%g\t%g\n", iter, admf.lam_u_, admf.lam_v_, admf.lam_bu_, admf.lam_bv_);

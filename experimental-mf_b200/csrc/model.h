@@ -7,9 +7,12 @@
 //   * theta_/phi_/bu_/bv_ are host copies: pull() refreshes them from the device, push() uploads
 //     edits.  read_model() pushes, save_model() pulls, so checkpoint code needs no change.
 //   * the training file is parsed ONCE (ingest) instead of once per epoch (mf.h:38-45);
-//   * `--fly N` keeps its meaning "how many updates may be in flight": N == 1 selects the ordered
-//     schedule (the reference's single-thread update order, bit-exact with the CPU oracle), N > 1
-//     the parallel schedule with at most N simultaneous updates of the hottest item row;
+//   * `--fly 1` selects the ordered schedule (the reference's single-thread update order, bit-exact with
+//     the CPU oracle); any `--fly N > 1` - the reference's default is 8 - selects the parallel production
+//     schedule at the width the library's own bounds allow (what bench.py measures).  The reference's N
+//     CPU threads have no counterpart on a GPU; MF_ROW_CONCURRENCY overrides the hot-row budget;
+//   * save_model() also writes `<file>.state` (round, eta0, gam): read_model() picks it up, and the run()
+//     drivers then continue with the NEXT round's step size instead of starting over;
 //   * errors are reported (message + exit code 3) instead of being ignored.
 #ifndef MFB_MODEL_H
 #define MFB_MODEL_H
@@ -68,6 +71,10 @@ class MF {
 
   // ---- B200 side ----
   mfb_ctx* ctx_;
+  int start_round_;       // rounds already applied to a model loaded with its .state sidecar (0: fresh)
+  void write_state(const char* file, int round) const;
+  bool read_state(const char* file);
+  void apply_options();   // MF_ROW_CONCURRENCY, model age of a resumed run
   int train_ds_;          // the training file as SoA tiles in HBM
   int device_;
   void pull();            // HBM -> theta_/phi_/bu_/bv_
@@ -127,6 +134,9 @@ class AdaptRegMF : public MF {
   int loss_, measure_;
   float lam_u_, lam_v_, lam_bu_, lam_bv_;  // refreshed from the device after every epoch
   // ---- B200 side ----
+  // the evaluation `--measure` selects: 0 = MF::calc_mse as the reference runs it (the link of --loss ignored,
+  // model.cc:62), 1 = the prediction goes through active() first (util.h:90-95) - what --loss 1 trains for
+  float calc_measure(const mf::Blocks& blocks, int& ndata);
   void admf_epoch();      // AdRegFilter over the whole file + one updateReg per user
 };
 

@@ -64,10 +64,13 @@ SIGNATURES = {
     "mfb_dataset_num_blocks": (C.c_int64, [C.c_void_p, C.c_int]),
     "mfb_sgd_epoch_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float,
                                           C.c_float, C.c_int, C.c_int64]),
+    "mfb_sgd_epoch_from_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64,
+                                          C.POINTER(C.c_int64)]),
     "mfb_dataset_refresh_from_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mfb_blocks_pin": (C.c_int, [C.c_void_p]),
     "mfb_blocks_unpin": (C.c_int, [C.c_void_p]),
     "mfb_sse": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "mfb_sse_link": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mfb_seteta": (C.c_float, [C.c_float, C.c_int, C.c_float]),
     "mfb_seteta_cutoff": (C.c_float, [C.c_float, C.c_int, C.c_float, C.c_float]),
     "mfb_dp_weights": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
@@ -84,6 +87,7 @@ SIGNATURES = {
     "mfb_admf_epoch": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]),
     "mfb_blocks_split_by_item": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p)]),
     "mfb_blocks_merge_runs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mfb_blocks_regroup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -206,6 +210,11 @@ class Blocks:
     def merge_runs(self, users_per_block=500):
         out = C.c_void_p()
         _check(lib().mfb_blocks_merge_runs(self.h, users_per_block, C.byref(out)))
+        return Blocks(out)
+
+    def regroup(self, merge_users=True, longest_first=True, users_per_block=500):
+        out = C.c_void_p()
+        _check(lib().mfb_blocks_regroup(self.h, int(merge_users), int(longest_first), users_per_block, C.byref(out)))
         return Blocks(out)
 
     @property
@@ -389,6 +398,12 @@ class Context:
     def dataset_refresh_from_host(self, ds, blocks):
         _check(lib().mfb_dataset_refresh_from_host(self.h, ds, blocks.h))
 
+    def sgd_epoch_from_file(self, path, eta, lam, gb, mode=MODE_ATOMIC, tile_ratings=0):
+        """one out-of-core epoch over the rating file at `path`; returns the number of records processed"""
+        n = C.c_int64()
+        _check(lib().mfb_sgd_epoch_from_file(self.h, path.encode(), eta, lam, gb, mode, tile_ratings, C.byref(n)))
+        return n.value
+
     def sgd_epoch_from_host(self, ds, blocks, eta, lam, gb, mode=MODE_HOGWILD, chunk_ratings=0):
         _check(lib().mfb_sgd_epoch_from_host(self.h, ds, blocks.h, eta, lam, gb, mode, chunk_ratings))
 
@@ -475,9 +490,9 @@ class Context:
         _check(lib().mfb_comm_allreduce_sse(self.h, C.byref(s), C.byref(k)))
         return s.value, k.value
 
-    def sse(self, ds, gb):
+    def sse(self, ds, gb, link=0):
         s, n = C.c_double(), C.c_int64()
-        _check(lib().mfb_sse(self.h, ds, gb, C.byref(s), C.byref(n)))
+        _check(lib().mfb_sse_link(self.h, ds, gb, link, C.byref(s), C.byref(n)))
         return s.value, n.value
 
     def rmse(self, ds, gb):

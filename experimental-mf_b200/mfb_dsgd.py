@@ -38,6 +38,11 @@ def piece_schedule(rank, world, halves=1, rotations=1):
     return [(r, ((rank + s) % world) * halves + h) for r in range(rotations) for s in range(world) for h in range(halves)]
 
 
+def turn_blocks(nblocks, turn, rotations):
+    """Blocks [k0, k1) of a cell that turn `turn` of `rotations` works on (mfb_dsgd_epoch_ex)."""
+    return nblocks * turn // rotations, nblocks * (turn + 1) // rotations
+
+
 class DsgdWorker:
     """This rank's shard of the model and data on its GPU, plus the NCCL ring."""
 

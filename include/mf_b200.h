@@ -72,9 +72,11 @@ int mfb_sync(mfb_ctx* ctx);
 /* tuning knobs (DESIGN.md "concurrency bounds"): "row_concurrency" (default 32: bound on the stale
  * updates of the hottest item row in flight at once, at eta = 0.02), "eta_scaling" (1: that bound
  * widens with 0.02/eta; 2: the run bound too; 0: off), "run_fraction_ppm" (default 3500: user-runs in
- * flight / user-runs of the file), "max_groups" (explicit number of runs in flight), "kernel" (0 =
- * choose, 1/2 = warp per run, 3 = sub-warp stream), "ring" (1..4), "throttle", "ctas_per_sm",
- * "threads", "memopt" */
+ * flight / user-runs of the file; applies during the first "run_bound_epochs" (default 1) epochs after the
+ * factors were set - "model_age" is that epoch count, kept by the library, settable by hosts that load a
+ * trained model or drive epochs slice by slice), "max_groups" (explicit number of runs in flight), "kernel"
+ * (0 = choose, 1 = generic warp per run, 3 = sub-warp stream, 4 = burst), "ring" (1..4), "throttle",
+ * "ctas_per_sm", "threads", "memopt" */
 int mfb_set_option(mfb_ctx* ctx, const char* name, int value);
 /* allocate the optional array groups: 1 = admf shadows (*_OLD), 2 = dpmf (UR, VR, LAMBDA_*) */
 int mfb_enable(mfb_ctx* ctx, int group);
@@ -174,6 +176,14 @@ int64_t mfb_dataset_num_blocks(mfb_ctx* ctx, int ds);
  * finalized dataset created from the same blocks; its HBM tiles are the copy target. */
 int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float eta, float lambda,
                             float gb, int mode, int64_t chunk_ratings);
+/* One epoch straight from the [u32 size][mf.Block] training FILE, nothing resident - the reference's own way of
+ * running an epoch (read -> parse -> update pipeline, main.cc:45-50, mf.h:24-69): frames are decoded by the host
+ * cores into pinned memory chunk by chunk (whole Blocks, about `tile_ratings` records, 0 = 8 Mi), copied into one
+ * of TWO device tile buffers and updated there while the next chunk is being decoded.  Device memory for ratings
+ * is 2 x tile_ratings x 8 bytes whatever the file size.  File order is kept: in the ORDERED schedule the result
+ * equals mfb_sgd_epoch on the loaded file bit for bit.  *ratings (optional) = records processed. */
+int mfb_sgd_epoch_from_file(mfb_ctx* ctx, const char* path, float eta, float lambda, float gb, int mode,
+                            int64_t tile_ratings, int64_t* ratings);
 /* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
  * the next epoch kernel on `ds` waits for the copy.  Used by the multi-GPU end-to-end path. */
 int mfb_dataset_refresh_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src);
@@ -184,6 +194,10 @@ int mfb_blocks_pin(mfb_blocks* b);
 int mfb_blocks_unpin(mfb_blocks* b);
 /* MF::calc_mse (model.cc:41-73): SUM of squared errors and the record count. */
 int mfb_sse(mfb_ctx* ctx, int ds, float gb, double* sse, int64_t* n);
+/* the same pass with the prediction sent through the link of --loss first: link 0 = identity (mfb_sse), 1 =
+ * logistic, active() of util.h:90-95 as the update (admf.h:69) and updateReg (model.h:87) apply it.  The reference's
+ * calc_mse ignores loss_ (model.cc:62) and never reads measure_ (model.h:109); `--measure 1` selects this here. */
+int mfb_sse_link(mfb_ctx* ctx, int ds, float gb, int link, double* sse, int64_t* n);
 /* MF::seteta (model.cc:36-38) / DPMF::seteta_cutoff (model.cc:350-352): same formula, host side */
 float mfb_seteta(float eta0, int round, float gam);
 float mfb_seteta_cutoff(float eta0, int round, float gam, float mineta);
@@ -240,6 +254,10 @@ int mfb_admf_epoch(mfb_ctx* ctx, int ds, float eta, float eta_reg, int loss, flo
 int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bounds, mfb_blocks** out);
 /* one run per user (its runs concatenated in file order, users in order of first appearance) */
 int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out);
+/* the general regrouping: merge_users != 0 as above; longest_first != 0: runs in descending order of length (a
+ * launch ends when its longest run still in flight ends: longest-processing-time-first scheduling).  Changes the
+ * order of updates: for epochs after the first, where the order no longer shows in the result. */
+int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, int users_per_block, mfb_blocks** out);
 int mfb_comm_unique_id(void* out128);
 int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
 int mfb_comm_destroy(mfb_ctx* ctx);

@@ -312,6 +312,35 @@ float mfo_sse(const mfo_model* m, const mfo_data* d, float gb, int64_t* ndata) {
   return sloss;
 }
 
+static float active(float val, int type);
+
+/* The evaluation that matches --loss: MF::calc_mse (model.cc:41-73) with the prediction sent through the link
+ * active() of util.h:90-95 first, exactly as the admf update (admf.h:69) and updateReg (model.h:87-88) form
+ * their residual: error = rating - active(sdot + bu + bv + gb, loss).  The reference's calc_mse itself ignores
+ * loss_ (model.cc:62) and measure_ is never read (model.h:109), so this is the SURVEY 8f-4 extension; loss = 0
+ * differs from mfo_sse only in the order of the additions. */
+float mfo_sse_link(const mfo_model* m, const mfo_data* d, float gb, int loss, int64_t* ndata) {
+  float sloss = 0.0f;
+  int64_t n = 0;
+  for (int64_t b = 0; b < d->nblocks; b++) {
+    float sl = 0.0f;
+    for (int64_t r = d->block_off[b]; r < d->block_off[b + 1]; r++) {
+      const int uid = d->run_uid[r];
+      const float* theta = m->theta + (size_t)uid * m->stride;
+      n += d->run_off[r + 1] - d->run_off[r];
+      for (int64_t k = d->run_off[r]; k < d->run_off[r + 1]; k++) {
+        const int vid = d->vid[k];
+        const float* phi = m->phi + (size_t)vid * m->stride;
+        float error = d->rating[k] - active(o_sdot(m->dim, theta, phi) + m->bu[uid] + m->bv[vid] + gb, loss);
+        sl += error * error;
+      }
+    }
+    sloss += sl;
+  }
+  if (ndata) *ndata = n;
+  return sloss;
+}
+
 /* ==================================== SGLD / DP ============================================ */
 /* model.cc:240-242 */
 float mfo_dp_bound(float epsilon, int tau) {

@@ -66,6 +66,8 @@ void mfo_sgd_epoch(mfo_model* m, const mfo_data* d, float eta, float lambda, flo
 /* ---- evaluation: MF::calc_mse, model.cc:41-73.  Returns the SUM of squared errors in fp32
  * (per-block fp32 partials added in block order == the reference with one OpenMP thread). */
 float mfo_sse(const mfo_model* m, const mfo_data* d, float gb, int64_t* ndata);
+/* calc_mse with the link of --loss applied to the prediction first (util.h:90-95, admf.h:69, model.h:87) */
+float mfo_sse_link(const mfo_model* m, const mfo_data* d, float gb, int loss, int64_t* ndata);
 
 /* ---- SGLD / DP: SgldFilter::operator(), dpmf.h:41-91, + model.cc:197-352 ---- */
 typedef struct {

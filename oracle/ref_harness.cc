@@ -36,6 +36,9 @@ struct Handle {
 };
 
 char* dup_or_null(const char* s) { return s ? strdup(s) : NULL; }
+// result_/model_ are `const char* const` members fixed by the constructors (model.h:24): the next ref_create_*
+// call passes these (ref_set_io_paths), so that save_model / read_model / read_hyper can be exercised
+char *g_result = NULL, *g_model = NULL;
 
 }  // namespace
 
@@ -52,7 +55,7 @@ void* ref_create_mf(const char* train, const char* test, int dim, float eta, flo
   h->train_path = dup_or_null(train);
   h->test_path = dup_or_null(test);
   h->valid_path = NULL;
-  h->mf = new MF(h->train_path, h->test_path, NULL, NULL, dim, 1, eta, gam, lambda, gb, nu, nv,
+  h->mf = new MF(h->train_path, h->test_path, g_result, g_model, dim, 1, eta, gam, lambda, gb, nu, nv,
                  /*fly*/ 1, /*stride*/ 2);
   h->dp = NULL;
   h->ad = NULL;
@@ -71,7 +74,7 @@ void* ref_create_dpmf(const char* train, const char* test, int dim, float eta, f
   h->train_path = dup_or_null(train);
   h->test_path = dup_or_null(test);
   h->valid_path = NULL;
-  h->dp = new DPMF(h->train_path, h->test_path, NULL, NULL, dim, 1, eta, gam, lambda, gb, nu, nv,
+  h->dp = new DPMF(h->train_path, h->test_path, g_result, g_model, dim, 1, eta, gam, lambda, gb, nu, nv,
                    1, 2, hypera, hyperb, epsilon, tau, noise_size, temp, mineta);
   h->mf = h->dp;
   h->ad = NULL;
@@ -242,6 +245,26 @@ void ref_admf_get_lams(void* hv, float* out4) {
   out4[2] = a->lam_bu_;
   out4[3] = a->lam_bv_;
 }
+
+// ---- checkpoints (model.cc:75-195) -------------------------------------------------------------
+void ref_set_io_paths(const char* result, const char* model) {
+  g_result = dup_or_null(result);
+  g_model = dup_or_null(model);
+}
+// MF::save_model / DPMF::save_model: writes "<result>_<round>"
+void ref_save_model(void* hv, int round) {
+  Handle* h = (Handle*)hv;
+  if (h->kind == K_DPMF) h->dp->save_model(round);
+  else h->mf->save_model(round);
+}
+// MF::read_model / DPMF::read_model from model_
+void ref_read_model(void* hv) {
+  Handle* h = (Handle*)hv;
+  if (h->kind == K_DPMF) h->dp->read_model();
+  else h->mf->read_model();
+}
+void ref_dpmf_read_hyper(void* hv) { ((Handle*)hv)->dp->read_hyper(); }
+float ref_get_lambda(void* hv) { return ((Handle*)hv)->mf->lambda_; }
 
 int ref_padding(int dim) { return padding(dim); }
 

@@ -17,12 +17,14 @@ import mfb_dsgd  # noqa: E402
 import oraclelib as ol  # noqa: E402
 
 NU, NV, NNZ, DIM, GB, EPOCHS = 400, 150, 20000, 16, 2.76, 2
+HALVES, FIRST_EPOCH_ROTATIONS = 2, 3  # pieces per item block; turns of the ring in epoch 1
 
 
 def cell_datasets(rank, world):
+    """this rank's cells, one per piece (world * HALVES of them), and the piece bounds"""
     u0, u1 = mfb_dsgd.user_range(NU, rank, world)
     tr, _, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.0, users_per_block=40, user_begin=u0, user_end=u1))
-    bounds = mfb_dsgd.item_bounds(NV, world)
+    bounds = mfb_dsgd.item_bounds(NV, world * HALVES)
     return [ol.Dataset(b.block_off, b.run_uid, b.run_off, b.vid, b.rating) for b in tr.split_by_item(bounds)], bounds
 
 
@@ -33,22 +35,26 @@ def main():
     cells, bounds = cell_datasets(rank, world)
     m = ol.Model(NU, NV, DIM, seed=3)  # same seeded start on every rank
     mm = m.as_mfo()
+    to, frm = (rank - 1) % world, (rank + 1) % world
     for ep in range(1, EPOCHS + 1):
         eta = mb.seteta(2e-2, ep, 1.0)
-        for b, to, frm in mfb_dsgd.dsgd_schedule(rank, world):
-            dd = cells[b].as_mfo()
+        rotations = FIRST_EPOCH_ROTATIONS if ep == 1 else 1
+        for turn, j in mfb_dsgd.piece_schedule(rank, world, HALVES, rotations):
+            k0, k1 = mfb_dsgd.turn_blocks(cells[j].nblocks, turn, rotations)
+            part = cells[j].block_range(k0, k1)  # (keep it alive: as_mfo() holds raw pointers)
+            dd = part.as_mfo()
             ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), eta, 5e-3, GB)
-            nb = (b + 1) % world
-            send = torch.from_numpy(np.ascontiguousarray(np.c_[m.phi[bounds[b]:bounds[b + 1]], m.bv[bounds[b]:bounds[b + 1]]]))
-            recv = torch.empty((bounds[nb + 1] - bounds[nb], m.stride + 1), dtype=torch.float32)
+            nj = (j + HALVES) % (world * HALVES)  # the same piece of the next block arrives from rank+1
+            send = torch.from_numpy(np.ascontiguousarray(np.c_[m.phi[bounds[j]:bounds[j + 1]], m.bv[bounds[j]:bounds[j + 1]]]))
+            recv = torch.empty((bounds[nj + 1] - bounds[nj], m.stride + 1), dtype=torch.float32)
             reqs = [dist.isend(send, to), dist.irecv(recv, frm)]
             for r in reqs:
                 r.wait()
-            m.phi[bounds[nb]:bounds[nb + 1]] = recv[:, :m.stride].numpy()
-            m.bv[bounds[nb]:bounds[nb + 1]] = recv[:, m.stride].numpy()
+            m.phi[bounds[nj]:bounds[nj + 1]] = recv[:, :m.stride].numpy()
+            m.bv[bounds[nj]:bounds[nj + 1]] = recv[:, m.stride].numpy()
     u0, u1 = mfb_dsgd.user_range(NU, rank, world)
     np.savez(os.path.join(out, "rank%d.npz" % rank), theta=m.theta[u0:u1], bu=m.bu[u0:u1],
-             phi=m.phi[bounds[rank]:bounds[rank + 1]], bv=m.bv[bounds[rank]:bounds[rank + 1]])
+             phi=m.phi[bounds[rank * HALVES]:bounds[(rank + 1) * HALVES]], bv=m.bv[bounds[rank * HALVES]:bounds[(rank + 1) * HALVES]])
     dist.barrier()
     dist.destroy_process_group()
 

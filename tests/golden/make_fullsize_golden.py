@@ -47,6 +47,10 @@ WORK = os.environ.get("MFGOLD_DIR", "/dev/shm/mfgold")
 OUT = os.path.join(HERE, "fullsize")
 DP_TEMP = 0.1       # run.py:22,34 sweeps temp = 1e-1
 ADMF_ETA_REG = 2e-3  # main.cc:104
+# --hyperb: with the reference's default (100, main.cc:99) the Gibbs step draws lambda_u ~ 2000 while the factors are
+# still near their 1e-2 initialisation, eta*ntrain*lambda_u >> 1 and the REFERENCE ITSELF ends in NaN at round 7-8
+# on this data (kept on record: fullsize/*_hb100.json).  1e4 keeps the prior precisions at O(10) and the run stable.
+HYPERB = float(os.environ.get("HYPERB", "1e4"))
 
 
 def paths(tag):
@@ -135,7 +139,7 @@ def dp_run(k, eps, seed, tag):
     temp = np.float32(DP_TEMP * bound)
     noise_size = 400_000_000
     t0 = time.time()
-    h = R.ref_create_dpmf(tp.encode(), sp.encode(), k, eta0, GAM, LAMBDA, GB, NU, NV, 1.0, 100.0, eps, 0, noise_size,
+    h = R.ref_create_dpmf(tp.encode(), sp.encode(), k, eta0, GAM, LAMBDA, GB, NU, NV, 1.0, HYPERB, eps, 0, noise_size,
                           temp, 1e-13)
     r = ol.Ref(h, NU, NV, k)
     th, ph, bu, bv = mb.seeded_model(NU, NV, k, MODEL_SEED)
@@ -149,7 +153,7 @@ def dp_run(k, eps, seed, tag):
                      "order (harness), noise from the reference's own table (noise_size %d) and generator seed %d"
                      % (tag, k, eps, noise_size, seed),
            "k": k, "epsilon": eps, "tau": ta.value, "bound": bd.value, "ntrain": nt.value, "eta0": float(eta0),
-           "temp": float(temp), "gam": GAM, "gb": GB, "mineta": 1e-13, "hyper_a": 1.0, "hyper_b": 100.0,
+           "temp": float(temp), "gam": GAM, "gb": GB, "mineta": 1e-13, "hyper_a": 1.0, "hyper_b": HYPERB,
            "noise_seed": seed, "eta": [], "train_rmse": [], "test_rmse": [], "lambda_r": [], "lambda_ub": [],
            "lambda_vb": [], "lambda_u_mean": [], "lambda_v_mean": [], "seconds": []}
     for ep in range(1, EPOCHS + 1):
@@ -173,7 +177,7 @@ def dp_run(k, eps, seed, tag):
         out["seconds"].append(time.time() - t0)
         print(tag, "round", ep, "RMSE %.5f tRMSE %.5f lambda_r %.4f %.0fs" % (
             out["train_rmse"][-1], out["test_rmse"][-1], hyp[0], out["seconds"][-1]), flush=True)
-        save("%s_seed%d" % (tag, seed), out)
+        save("%s_seed%d%s" % (tag, seed, "" if HYPERB == 1e4 else "_hb%g" % HYPERB), out)
 
 
 def c4ad():

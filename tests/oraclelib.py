@@ -91,6 +91,8 @@ def oracle():
                                     C.c_float]
         L.mfo_sse.restype = C.c_float
         L.mfo_sse.argtypes = [C.POINTER(MfoModel), C.POINTER(MfoData), C.c_float, i64p]
+        L.mfo_sse_link.restype = C.c_float
+        L.mfo_sse_link.argtypes = [C.POINTER(MfoModel), C.POINTER(MfoData), C.c_float, C.c_int, i64p]
         L.mfo_dp_bound.restype = C.c_float
         L.mfo_dp_bound.argtypes = [C.c_float, C.c_int]
         L.mfo_dp_weights.restype = C.c_int32
@@ -160,6 +162,12 @@ def ref():
         L.ref_admf_get_lams.argtypes = [C.c_void_p, f32p]
         L.ref_num_valid.argtypes = [C.c_void_p]
         L.ref_get_valid.argtypes = [C.c_void_p, i32p, i32p, f32p]
+        L.ref_set_io_paths.argtypes = [C.c_char_p, C.c_char_p]
+        L.ref_save_model.argtypes = [C.c_void_p, C.c_int]
+        L.ref_read_model.argtypes = [C.c_void_p]
+        L.ref_dpmf_read_hyper.argtypes = [C.c_void_p]
+        L.ref_get_lambda.restype = C.c_float
+        L.ref_get_lambda.argtypes = [C.c_void_p]
         L.ref_srand.argtypes = [C.c_uint]
         L.ref_seed_generator.argtypes = [C.c_uint]
         L.ref_padding.argtypes = [C.c_int]
@@ -193,6 +201,13 @@ class Dataset:
     def as_mfo(self):
         return MfoData(self.nblocks, _p(self.block_off, i64p), self.nruns, _p(self.run_uid, i32p),
                        _p(self.run_off, i64p), _p(self.vid, i32p), _p(self.rating, f32p))
+
+    def block_range(self, k0, k1):
+        """Blocks [k0, k1) of the file as a Dataset of their own (a slice of an epoch)."""
+        r0, r1 = int(self.block_off[k0]), int(self.block_off[k1])
+        o0, o1 = int(self.run_off[r0]), int(self.run_off[r1])
+        return Dataset(self.block_off[k0:k1 + 1] - r0, self.run_uid[r0:r1], self.run_off[r0:r1 + 1] - o0,
+                       self.vid[o0:o1], self.rating[o0:o1])
 
     def uid_per_rating(self):
         return np.repeat(self.run_uid, np.diff(self.run_off))

@@ -84,17 +84,62 @@ def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib)
     m = ol.Model(w.NU, w.NV, w.DIM, seed=3)
     mm = m.as_mfo()
     cells = [w.cell_datasets(r, world)[0] for r in range(world)]
+    H = w.HALVES
     for ep in range(1, w.EPOCHS + 1):
         eta = mb.seteta(2e-2, ep, 1.0)
-        for s in range(world):  # cells of one sub-epoch share no user and no item: any order
+        rotations = w.FIRST_EPOCH_ROTATIONS if ep == 1 else 1
+        scheds = [mfb_dsgd.piece_schedule(r, world, H, rotations) for r in range(world)]
+        for step in range(len(scheds[0])):  # pieces worked on at the same step share no user and no item: any order
+            assert len({scheds[r][step][1] for r in range(world)}) == world
             for r in range(world):
-                dd = cells[r][mfb_dsgd.dsgd_schedule(r, world)[s][0]].as_mfo()
+                turn, j = scheds[r][step]
+                k0, k1 = mfb_dsgd.turn_blocks(cells[r][j].nblocks, turn, rotations)
+                part = cells[r][j].block_range(k0, k1)  # (keep it alive: as_mfo() holds raw pointers)
+                dd = part.as_mfo()
                 oracle_lib.mfo_sgd_epoch(C.byref(mm), C.byref(dd), eta, 5e-3, w.GB)
-    bounds = mfb_dsgd.item_bounds(w.NV, world)
+    bounds = mfb_dsgd.item_bounds(w.NV, world * H)
     for r in range(world):
         got = np.load(tmp_path / ("rank%d.npz" % r))
         u0, u1 = mfb_dsgd.user_range(w.NU, r, world)
         np.testing.assert_array_equal(got["theta"], m.theta[u0:u1])
         np.testing.assert_array_equal(got["bu"], m.bu[u0:u1])
-        np.testing.assert_array_equal(got["phi"], m.phi[bounds[r]:bounds[r + 1]])  # block r is home again
-        np.testing.assert_array_equal(got["bv"], m.bv[bounds[r]:bounds[r + 1]])
+        np.testing.assert_array_equal(got["phi"], m.phi[bounds[r * H]:bounds[(r + 1) * H]])  # block r is home again
+        np.testing.assert_array_equal(got["bv"], m.bv[bounds[r * H]:bounds[(r + 1) * H]])
+
+
+def test_piece_schedule_covers_every_cell_once_per_turn_and_never_shares_items():
+    for P in (1, 2, 3, 8):
+        for H in (1, 2):
+            for R in (1, 4):
+                sch = [mfb_dsgd.piece_schedule(r, P, H, R) for r in range(P)]
+                assert all(len(x) == R * P * H for x in sch)
+                for step in range(R * P * H):
+                    assert len({sch[r][step][1] for r in range(P)}) == P      # disjoint pieces at every step
+                    assert len({sch[r][step][0] for r in range(P)}) == 1      # all ranks in the same turn
+                for r in range(P):
+                    for t in range(R):
+                        assert sorted(j for tt, j in sch[r] if tt == t) == list(range(P * H))
+                    assert sch[r][0][1] == r * H                              # a turn starts with the home block
+                    for step in range(R * P * H - H):                         # what I work on H steps later is what rank+1 holds now
+                        assert sch[r][step + H][1] == sch[(r + 1) % P][step][1]
+    assert mfb_dsgd.turn_blocks(10, 0, 3) == (0, 3) and mfb_dsgd.turn_blocks(10, 2, 3) == (6, 10)
+
+
+def test_regroup_longest_first_keeps_every_record_and_sorts_runs():
+    nu, nv = 400, 90
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 20000, test_frac=0.0, users_per_block=50))
+    cell = tr.split_by_item(np.array([0, 45, 90], np.int32))[0]
+    for merge in (False, True):
+        g = cell.regroup(merge_users=merge, longest_first=True, users_per_block=64)
+        lens = np.diff(g.run_off)
+        assert g.nratings == cell.nratings and (lens > 0).all() and (np.diff(lens) <= 0).all()
+        assert g.nruns == (len(np.unique(cell.run_uid)) if merge else cell.nruns)
+        assert list(g.block_off) == list(range(0, g.nruns, 64)) + [g.nruns]
+        ku = np.repeat(g.run_uid, lens).astype(np.int64) * nv + g.vid
+        kc = np.repeat(cell.run_uid, np.diff(cell.run_off)).astype(np.int64) * nv + cell.vid
+        assert sorted(ku.tolist()) == sorted(kc.tolist())
+        # a user's records keep their file order
+        u = g.run_uid[0]
+        cu = np.repeat(cell.run_uid, np.diff(cell.run_off))
+        if merge:
+            np.testing.assert_array_equal(g.vid[:lens[0]], cell.vid[cu == u])

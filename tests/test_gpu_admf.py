@@ -137,3 +137,26 @@ def test_parallel_admf_tracks_serial_oracle_ml1m_shape():
     assert abs(got[-1] - want[-1]) <= 2e-3
     np.testing.assert_allclose(lg[-1], lw[-1], rtol=0.1, atol=2e-4)
     c.close()
+
+
+def test_link_aware_evaluation_pass_matches_oracle():
+    """mfb_sse_link (the evaluation `--measure 1` selects for `--loss 1`) vs the oracle's restatement."""
+    import ctypes as C
+    nu, nv, dim = 300, 120, 64
+    train, test, _ = ol.make_ratings(nu, nv, 9000, seed=12)
+    r01 = (test.rating > 3).astype(np.float32)
+    t01 = ol.Dataset(test.block_off, test.run_uid, test.run_off, test.vid, r01)
+    m = ol.Model(nu, nv, dim, seed=3, scale=0.3)
+    c = ctx_from_model(m)
+    d01, d = upload_ds(c, t01), upload_ds(c, test)
+    n = C.c_int64()
+    mm = m.as_mfo()
+    want1 = ol.oracle().mfo_sse_link(C.byref(mm), C.byref(t01.as_mfo()), GB, 1, C.byref(n))
+    got1, n1 = c.sse(d01, GB, link=1)
+    assert n1 == n.value and abs(got1 - want1) <= 2e-6 * want1
+    want0 = ol.oracle().mfo_sse(C.byref(mm), C.byref(test.as_mfo()), GB, C.byref(n))
+    got0, _ = c.sse(d, GB, link=0)
+    assert abs(got0 - want0) <= 2e-6 * want0
+    with pytest.raises(mb.MfbError):
+        c.sse(d, GB, link=2)
+    c.close()

@@ -2,6 +2,9 @@
 datasets walked in schedule order (what P GPUs execute, serialised) against the CPU oracle walking
 the same schedule.  The real multi-rank run is tools/dsgd_check.py (torchrun, >= 2 GPUs)."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -61,3 +64,21 @@ def test_cell_schedule_on_one_gpu_equals_oracle_schedule(world):
                 oracle_sgd(m, cells_cpu[r][b], eta, 5e-3, GB)
     assert model_equal(c, m)
     c.close()
+
+
+def test_multi_rank_ring_is_bit_exact_with_the_oracle_walking_the_same_schedule():
+    """The real thing, on every visible GPU pair: one process per GPU, ordered cells, half-block shifts over
+    NCCL overlapped with the other half's kernel, three ring turns in epoch 1 - the factors of every rank must
+    equal the CPU oracle walking the same schedule of pieces, bit for bit (tools/dsgd_check.py exits 1 if not)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 4 if n >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tools", "dsgd_check.py")],
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    print(out.stdout[-3000:])
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "bit-exact vs oracle schedule walk: True" in out.stdout

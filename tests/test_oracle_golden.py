@@ -149,3 +149,25 @@ def test_wire_reader_matches_reference_bytes(oracle_lib, golden, tmp_path):
     q = tmp_path / "again.bin"
     ds.write(str(q))
     assert q.read_bytes() == p.read_bytes()
+
+
+def test_link_aware_evaluation_matches_numpy(oracle_lib):
+    """SURVEY 8f-4: calc_mse with the logistic link of --loss 1 (util.h:90-95) applied to the prediction, vs numpy;
+    link 0 equals MF::calc_mse up to the order of the additions."""
+    import ctypes as C
+    nu, nv, dim = 90, 40, 24
+    train, test, _ = ol.make_ratings(nu, nv, 3000, seed=4)
+    m = ol.Model(nu, nv, dim, seed=8, scale=0.4)
+    mm, tt = m.as_mfo(), test.as_mfo()
+    n = C.c_int64()
+    u = test.uid_per_rating()
+    pred = np.einsum("ij,ij->i", m.theta[u, :dim].astype(np.float64), m.phi[test.vid, :dim].astype(np.float64)) \
+        + m.bu[u] + m.bv[test.vid] + 2.76
+    r01 = (test.rating > 3).astype(np.float32)          # a 0/1 target, what the logistic link is for
+    t01 = ol.Dataset(test.block_off, test.run_uid, test.run_off, test.vid, r01)
+    s1 = oracle_lib.mfo_sse_link(C.byref(mm), C.byref(t01.as_mfo()), 2.76, 1, C.byref(n))
+    want1 = float(((r01 - 1.0 / (1.0 + np.exp(-pred))) ** 2).sum())
+    assert n.value == test.nratings and abs(s1 - want1) <= 1e-5 * want1
+    s0 = oracle_lib.mfo_sse_link(C.byref(mm), C.byref(tt), 2.76, 0, C.byref(n))
+    ref0 = oracle_lib.mfo_sse(C.byref(mm), C.byref(tt), 2.76, C.byref(n))
+    assert abs(s0 - ref0) <= 1e-5 * ref0

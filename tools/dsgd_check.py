@@ -30,36 +30,42 @@ tr, te, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=u0,
 m = ol.Model(NU, NV, DIM, seed=11)
 th, ph = m.dense()
 bu0, bv0 = m.bu.copy(), m.bv.copy()  # rank 0 trains `m` in place below
-w = mfb_dsgd.DsgdWorker(NU, NV, DIM, rank, world, local, tr, te, unique_id)
+H, R1 = int(os.environ.get("HALVES", "2")), int(os.environ.get("ROTATIONS", "3"))
+w = mfb_dsgd.DsgdWorker(NU, NV, DIM, rank, world, local, tr, te, unique_id, halves=H, first_epoch_rotations=R1)
 w.ctx.set_factors(th, ph, m.bu, m.bv)
-for ep in (1, 2):
-    w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
-w.ctx.allgather_items(w.bounds)
+rots = [w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED) for ep in (1, 2)]
+w.ctx.allgather_items(w.home_bounds)
 theta, phi, bu, bv = w.ctx.get_factors()
 mine = torch.from_numpy(np.ascontiguousarray(theta)).cuda()
 allth = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(allth, mine)
 ok = True
 if rank == 0:
-    # the oracle walks the same cell schedule (cells of one sub-epoch are disjoint)
+    # the oracle walks the same schedule of pieces (pieces worked on at the same step share no user and no item)
     cells = []
     for r in range(world):
         a, b = mfb_dsgd.user_range(NU, r, world)
         t, _, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=a, user_end=b))
         cells.append([ol.Dataset(p.block_off, p.run_uid, p.run_off, p.vid, p.rating) for p in t.split_by_item(w.bounds)])
     mm = m.as_mfo()
-    for ep in (1, 2):
-        for s in range(world):
+    for ep, rot in zip((1, 2), rots):
+        scheds = [mfb_dsgd.piece_schedule(r, world, w.halves, rot) for r in range(world)]
+        for step in range(len(scheds[0])):
             for r in range(world):
-                dd = cells[r][mfb_dsgd.dsgd_schedule(r, world)[s][0]].as_mfo()
+                turn, j = scheds[r][step]
+                k0, k1 = mfb_dsgd.turn_blocks(cells[r][j].nblocks, turn, rot)
+                part = cells[r][j].block_range(k0, k1)
+                dd = part.as_mfo()
                 ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
     ok &= np.array_equal(phi, m.phi[:, :DIM]) and np.array_equal(bv, m.bv)
     for r in range(world):
         a, b = mfb_dsgd.user_range(NU, r, world)
         ok &= np.array_equal(allth[r].cpu().numpy()[a:b], m.theta[a:b, :DIM])
-    print("DSGD ordered, %d ranks: bit-exact vs oracle schedule walk: %s" % (world, ok), flush=True)
+    print("DSGD ordered, %d ranks, %d pieces per block, %s ring turns in epochs 1, 2: bit-exact vs oracle schedule walk: %s" % (
+        world, w.halves, rots, ok), flush=True)
 # parallel schedule: RMSE after 10 epochs vs the serial oracle
 w.ctx.set_factors(th, ph, bu0, bv0)
+w.epochs_done = 0
 traj = []
 for ep in range(1, 11):
     w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ATOMIC)

@@ -43,13 +43,18 @@ def interleaved(W):
     order = np.argsort(key, kind="stable")
     return ol.Dataset(np.array([0, n], np.int64), run_uid[rec_run[order]].astype(np.int32), np.arange(n + 1, dtype=np.int64),
                       vid[order], rating[order])
+# FILE_EPOCHS=a-b: epochs a..b (1-based, inclusive) run in file order instead (where does the order effect arise?)
+fe = os.environ.get("FILE_EPOCHS")
+fe = [int(x) for x in fe.split("-")] if fe else None
+plain = interleaved(1)
 for W in [int(x) for x in (sys.argv[1:] or ["1", "1680", "6720"])]:
     ds = interleaved(W)
     m = ol.Model(nu, nv, k, seed=11)
-    mm, dd, tt = m.as_mfo(), ds.as_mfo(), test.as_mfo()
+    mm, tt = m.as_mfo(), test.as_mfo()
     traj = []
     t0 = time.time()
     for ep in range(1, EPOCHS + 1):
+        dd = (plain if fe and fe[0] <= ep <= fe[1] else ds).as_mfo()
         ol.oracle().mfo_sgd_epoch(C.byref(mm), C.byref(dd), mb.seteta(2e-2, ep, 1.0), 5e-3, GB)
         cnt = C.c_int64(); s = ol.oracle().mfo_sse(C.byref(mm), C.byref(tt), GB, C.byref(cnt)); traj.append(float(np.sqrt(s / cnt.value)))
-    print("W %5d: rmse %s  (%.0f s)" % (W, " ".join("%.4f" % x for x in traj), time.time() - t0), flush=True)
+    print("W %5d file-epochs %s: rmse %s  (%.0f s)" % (W, fe, " ".join("%.4f" % x for x in traj), time.time() - t0), flush=True)
