@@ -4,7 +4,8 @@
 //   getdata -r raw.txt   -w user.txt  --method userwise --split S      (getdata.cc:21-80,157-164)
 //   getdata -r user.txt  -w train.bin --method protobuf --size B       (getdata.cc:82-126)
 //   getdata              -w prefix    --method synth --nu U --nv V --nnz N [--split S --size B
-//                                      --test F --valid F --seed X]     (new: prefix.train/.test/.valid)
+//                                      --test F --valid F --seed X --head M]  (new: prefix.train/.test/.valid;
+//                                      --head M keeps the first Blocks of the training file, M ratings or more)
 //
 // raw.txt: first line the record count, then "user,item,rating,timestamp" lines (getdata.cc:21-32).
 // user.txt: "uid:" lines each followed by "vid,rating" lines (getdata.cc:39-50).
@@ -20,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -148,6 +150,7 @@ int main(int argc, char** argv) {
   long long nu = 0, nv = 0, nnz = 0;
   double test = 0.01, valid = 0.0;
   uint64_t seed = 0;
+  long long head = 0;
   for (int i = 1; i < argc; i++) {
     auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
     if (!strcmp(argv[i], "-r")) read = next();
@@ -161,6 +164,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--test")) test = atof(next());
     else if (!strcmp(argv[i], "--valid")) valid = atof(next());
     else if (!strcmp(argv[i], "--seed")) seed = strtoull(next(), nullptr, 0);
+    else if (!strcmp(argv[i], "--head")) head = atoll(next());
     else {
       printf("unknown parameters.\n\n");
       hint();
@@ -191,7 +195,23 @@ int main(int argc, char** argv) {
     p.valid_frac = (float)valid;
     if (seed) p.seed = seed;
     mfb_blocks *tr = nullptr, *te = nullptr, *va = nullptr;
+    if (head > 0 && head < nnz) {  // the sample needs only the users of its Blocks (the generator shards by user;
+      // a user's ratings are dealt over `split` chunks, so a prefix of M ratings needs ~split*M/nnz of the users)
+      const double frac = std::min(1.0, 1.3 * p.split * (double)head / (double)nnz + 0.01);
+      p.user_end = std::max<int32_t>(1, (int32_t)(nu * frac));
+    }
     if (mfb_generate(&p, &tr, &te, &va)) return die("generate");
+    if (head > 0 && head < mfb_blocks_num_ratings(tr)) {
+      const int64_t* bo = mfb_blocks_block_off(tr);
+      const int32_t* ro = mfb_blocks_run_off(tr);
+      int64_t nb = 0;
+      while (nb < mfb_blocks_num_blocks(tr) && ro[bo[nb]] < head) nb++;
+      mfb_blocks* cut = nullptr;
+      if (mfb_blocks_from_arrays(nb, bo, bo[nb], mfb_blocks_run_uid(tr), ro, mfb_blocks_vid(tr), mfb_blocks_rating(tr), &cut))
+        return die("head");
+      mfb_blocks_free(tr);
+      tr = cut;
+    }
     const std::string base(write);
     int rc = mfb_blocks_write(tr, (base + ".train").c_str());
     if (!rc) rc = mfb_blocks_write(te, (base + ".test").c_str());

@@ -772,6 +772,22 @@ int64_t mfb_dataset_num_runs(mfb_ctx* h, int ds) {
   return d ? (d->finalized ? d->nruns : (int64_t)d->h_run_uid.size()) : -1;
 }
 
+// two device staging buffers for packed (3-byte) records on their way to the SoA tiles
+static int ensure_stage(Context* c, int64_t capacity) {
+  if (c->stage_capacity >= capacity) return MFB_OK;
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) MFB_CUDA(cudaStreamSynchronize(c->copy_stream));
+  c->stage_capacity = capacity;
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->d_stage_vid[b]);
+    cudaFree(c->d_stage_code[b]);
+    MFB_CUDA(cudaMalloc(&c->d_stage_vid[b], c->stage_capacity * sizeof(uint16_t)));
+    MFB_CUDA(cudaMalloc(&c->d_stage_code[b], c->stage_capacity));
+  }
+  if (!c->d_dict) MFB_CUDA(cudaMalloc(&c->d_dict, 256 * sizeof(float)));
+  return MFB_OK;
+}
+
 // ---- hot path -----------------------------------------------------------------------------------
 int mfb_sgd_epoch(mfb_ctx* h, int ds, float eta, float lambda, float gb, int mode) {
   MFB_REQUIRE(h, "ctx is NULL");
@@ -864,18 +880,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   MFB_CUDA(cudaStreamWaitEvent(c->stream2, start_ev, 0));
   const bool packed = s->packed && c->opt_packed_h2d;
   if (packed) {
-    if (c->stage_capacity < max_chunk + 65536) {
-      MFB_CUDA(cudaStreamSynchronize(c->stream));
-      MFB_CUDA(cudaStreamSynchronize(c->copy_stream));
-      c->stage_capacity = max_chunk + 65536;
-      for (int b = 0; b < 2; b++) {
-        cudaFree(c->d_stage_vid[b]);
-        cudaFree(c->d_stage_code[b]);
-        MFB_CUDA(cudaMalloc(&c->d_stage_vid[b], c->stage_capacity * sizeof(uint16_t)));
-        MFB_CUDA(cudaMalloc(&c->d_stage_code[b], c->stage_capacity));
-      }
-      if (!c->d_dict) MFB_CUDA(cudaMalloc(&c->d_dict, 256 * sizeof(float)));
-    }
+    if (int src = ensure_stage(c, max_chunk + 65536)) return src;
     MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
   }
   cudaStream_t const main_stream = c->stream;
@@ -970,9 +975,26 @@ int mfb_dataset_refresh_from_host(mfb_ctx* h, int ds, const mfb_blocks* src) {
     MFB_CUDA(cudaMemcpyAsync(d->d_run_uid, s->h_run_uid.data(), d->nruns * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(d->d_run_off, s->h_run_off.data(), (d->nruns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
   }
-  if (d->nratings) {
+  c->h2d_bytes += d->nruns * 8 + 4;
+  if (d->nratings && s->packed && c->opt_packed_h2d) {
+    // the compact records (u16 item id + u8 rating code, mfb_blocks_pin) into a staging buffer, expanded on the copy
+    // stream; stream order frees a staging buffer for the copy after next
+    if (int src = ensure_stage(c, d->nratings)) return src;
+    const int sb = c->stage_flip;
+    c->stage_flip ^= 1;
+    MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(c->d_stage_vid[sb], s->p_vid, d->nratings * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code, d->nratings, cudaMemcpyHostToDevice, c->copy_stream));
+    cudaStream_t const main_stream = c->stream;
+    c->stream = c->copy_stream;
+    const int urc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid, d->d_rating, d->nratings);
+    c->stream = main_stream;
+    if (urc) return urc;
+    c->h2d_bytes += d->nratings * 3;
+  } else if (d->nratings) {
     MFB_CUDA(cudaMemcpyAsync(d->d_vid, s->h_vid.data(), d->nratings * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(d->d_rating, s->h_rating.data(), d->nratings * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    c->h2d_bytes += d->nratings * 8;
   }
   MFB_CUDA(cudaEventRecord(d->refreshed, c->copy_stream));
   d->refresh_pending = true;
@@ -1126,9 +1148,12 @@ int mfb_sgld_epoch(mfb_ctx* h, int ds, const mfb_sgld_params* p, float gb, int m
   }
   MFB_CUDA(cudaSetDevice(c->device));
   begin_timing(c);
+  // (dpmf keeps the run bound in every epoch: its parity was established with it)
+  const int age = c->model_age;
+  c->model_age = 0;
   rc = d->nruns ? launch_sgld(c, d, p, gb, mode) : MFB_OK;
+  c->model_age = age + (rc == MFB_OK ? 1 : 0);
   end_timing(c);
-  if (rc == MFB_OK) c->model_age++;
   return rc;
 }
 
@@ -1266,9 +1291,13 @@ int mfb_admf_epoch(mfb_ctx* h, int ds, float eta, float eta_reg, int loss, float
   MFB_REQUIRE(loss == 0 || loss == 1, "loss must be 0 (least squares) or 1 (logistic)");
   MFB_CUDA(cudaSetDevice(c->device));
   begin_timing(c);
+  // admf keeps the run bound in every epoch: the regularisers are learned from the same stale rows, and with the
+  // bound lifted after epoch 1 the ML-1M-shaped run diverges (measured, round 2)
+  const int age = c->model_age;
+  c->model_age = 0;
   int rc = d->nruns ? launch_admf(c, d, eta, eta_reg, loss, gb, mode) : MFB_OK;
+  c->model_age = age + (rc == MFB_OK ? 1 : 0);
   end_timing(c);
-  if (rc == MFB_OK) c->model_age++;
   return rc;
 }
 

@@ -93,6 +93,7 @@ struct Context {
   uint8_t* d_stage_code[2] = {nullptr, nullptr};
   float* d_dict = nullptr;  // [256]
   int64_t stage_capacity = 0;
+  int stage_flip = 0;               // which staging buffer the next packed refresh uses
 
   bool timed = false;
   int64_t launches = 0;
@@ -133,8 +134,12 @@ struct Context {
   int opt_depth = 1;            // burst kernel: batches requested ahead (1 or 2)
   int opt_ring = 0;             // streaming kernel: item rows in flight per sub-warp (1..4; 0 = choose the
                                 // deepest ring the budget of the hottest row leaves room for)
-  int opt_row_concurrency = 32; // bound on the stale updates of the hottest item row in flight at once,
-                                // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t
+  int opt_row_concurrency = 16; // bound on the stale updates of the hottest item row in flight at once,
+                                // at eta = 0.02 (0 = none); see mfb_sgd_stream.cu launch_stream_t.  16 = eta * c <= 0.24
+                                // with the measured 0.75 rows per sub-warp.  Round 2, full sizes: 0.47 is stable in
+                                // epoch 1 (factors still small) but NOT later, when the bound has widened with 0.02/eta
+                                // and the factor norms have grown: NaN at 0.45-0.48 in DSGD cells from epoch 2 and on
+                                // the Yahoo shape on one GPU (37,888 sub-warps at epoch 5); 0.24 is stable in both
   int opt_packed_h2d = 1;       // streamed epochs send the compact 3-byte records when the blocks have them
   int opt_throttle = 0;         // streaming kernel: closed loop on the L2 reduction queue (mfb_sgd_stream.cu)
   int opt_eta_scaling = 1;      // scale that bound with 0.02/eta (the budget is on eta * count)
@@ -154,12 +159,16 @@ struct Context {
                                 // one gains nothing per run (251 warp instructions per step bound it) and costs width
   int opt_max_groups = 0;       // explicit cap on concurrent sub-warps (0 = derive from the above)
   int opt_run_fraction_ppm = 3500;  // user-runs in flight / user-runs of the file, parts per million (0 = no bound)
-  // ... which applies while the model is YOUNG: the order effect of interleaved runs is created in the first epoch,
-  // while the factors leave their random initialisation (tools/order_study.py: 5.6 % of the runs interleaved in
-  // every epoch: final tRMSE +1.7e-3; in every epoch but the first: +1e-4).  model_age counts the whole epochs
-  // applied since the factors were last set (init / upload); hosts that drive slices or load a trained model set it.
+  // The ORDER effect this bound is for is created in the first epoch, while the factors leave their random
+  // initialisation (tools/order_study.py, serial oracle: 5.6 % of the runs interleaved in every epoch: final tRMSE
+  // +1.7e-3; in every epoch but the first: +1e-4), so "run_bound_epochs" = n lifts it after n epochs.  It stays on
+  // in every epoch by default all the same: lifted, the wide launches of later epochs are UNSTABLE where it would
+  // matter (ML-1M shape: divergence from epoch 2 at any hot-row budget; DSGD cells: NaN above row_concurrency 16),
+  // and where they are stable nothing is gained (Netflix shape: the hardware width is reached either way; DSGD cells:
+  // 6.1 ms per rank and epoch with or without) - measured in round 2, gpurun_out/r2_cells2.log.
+  // model_age counts the whole epochs applied since the factors were last set (init / upload).
   int model_age = 0;
-  int opt_run_bound_epochs = 1;
+  int opt_run_bound_epochs = 1 << 30;
   std::vector<Dataset> datasets;
 };
 

@@ -424,7 +424,7 @@ namespace {
 // bound expressed as a count at the reference's default eta = 0.02 (main.cc:97).
 // (Full Netflix shape, epoch 1, round 2: 6,720 sub-warps with R = 1 - 24 stale updates of the hottest row by the
 // probe's 0.75 rows per sub-warp, eta*c = 0.47 - is stable; 11,348 - eta*c = 0.8 - ends in NaN.  A sub-warp with
-// R = 1 therefore counts for one whole row: row_concurrency = 32 then means eta*c <= 0.48 measured.)
+// R = 1 therefore counts for one whole row: row_concurrency = 16 means eta*c <= 0.24 measured; mfb_internal.h.)
 template <int R>
 constexpr double ring_weight() { return (double)R; }
 

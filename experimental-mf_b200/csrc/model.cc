@@ -134,7 +134,20 @@ float MF::calc_mse(const mf::Blocks& blocks, int& ndata) {  // model.cc:41-73: r
   return (float)sse;
 }
 
+// MF_TILE_RATINGS=n: out of core, as the reference runs (it re-reads and re-parses the training file every
+// epoch and never holds it, mf.h:24-69): the epoch goes straight from the file through two device tile buffers
+// of n ratings each (mfb_sgd_epoch_from_file); unset: the file is parsed once and stays resident in HBM
+static int64_t tile_ratings() {
+  const char* t = getenv("MF_TILE_RATINGS");
+  return t ? atoll(t) : 0;
+}
+
 void MF::sgd_epoch() {
+  if (tile_ratings() > 0) {
+    check(mfb_sgd_epoch_from_file(ctx_, train_data_, eta_, lambda_, gb_, schedule(), tile_ratings(), nullptr),
+          "mfb_sgd_epoch_from_file");
+    return;
+  }
   check(mfb_sgd_epoch(ctx_, train_ds_, eta_, lambda_, gb_, schedule()), "mfb_sgd_epoch");
 }
 
@@ -504,7 +517,7 @@ void run(MF& mf) {
   mf::Blocks blocks_test;
   plain_read(mf.test_data_, blocks_test);
   lap("test file");
-  mf.load_train();
+  if (tile_ratings() <= 0) mf.load_train();
   lap("training file (parse, ingest)");
   s = Time::now();
   for (int iter = mf.start_round_ + 1; iter <= mf.iter_; iter++) {  // (a model loaded with its .state continues)

@@ -113,10 +113,29 @@ class MfbError(RuntimeError):
     pass
 
 
+def _prefer_bundled_nccl():
+    """One NCCL per process: libmf_b200.so binds NCCL at run time (dlopen "libnccl.so.2", MFB_NCCL_LIB overrides).
+    In a Python process that later imports torch, a system libnccl loaded first would be the one torch then gets
+    (same SONAME) - and torch needs its own, newer one.  Point the library at the pip-installed copy torch uses."""
+    if os.environ.get("MFB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MFB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Load libmf_b200.so (fails loudly if it has not been built: run __graft_entry__.build())."""
     global _lib
     if _lib is None:
+        _prefer_bundled_nccl()
         if not os.path.exists(LIB_PATH):
             raise MfbError("%s not built (make -C experimental-mf_b200)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)

@@ -30,7 +30,10 @@ def dsgd_schedule(rank, world):
 
 
 FIRST_EPOCH_ROTATIONS = 16  # turns of the ring in epoch 1 (tools/dsgd_order_study.py)
-HALVES = 2                  # pieces per item block: the shift of one travels while the other is computed
+HALVES = 1                  # pieces per item block.  2 = the shift of one piece travels while the other is computed
+                            # (mfb_dsgd_epoch_ex); measured at P = 8 on the Netflix shape it costs more than it hides:
+                            # half-size blocks double the share of the hottest item in a cell and halve the run pieces
+                            # (10.4 ms of cell kernels per rank and epoch against 6.2), for 8 x ~0.1 ms of exposed shift
 
 
 def piece_schedule(rank, world, halves=1, rotations=1):
@@ -100,7 +103,8 @@ def bench(args, wl, shape, rank, world, local, config):
     """bench.py --gpus N (N > 1), launched by torch.distributed.run."""
     import torch
     import torch.distributed as dist
-    from bench import ETA0, GAM, GB, LAMBDA, METRIC, UNIT, ClockSampler, bytes_per_update, measured_peak
+    from bench import (ETA0, GAM, GB, LAMBDA, METRIC, RMSE_TOL, UNIT, ClockSampler, bytes_per_update, first_epoch_within, gold,
+                       measured_peak)
     nu, nv, nnz, k, test_frac = shape
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -119,6 +123,13 @@ def bench(args, wl, shape, rank, world, local, config):
     mode = {"hogwild": mb.MODE_HOGWILD, "atomic": mb.MODE_ATOMIC}[args.schedule]
     launches0 = w.ctx.launch_count()
     epoch = [0]
+    g = gold("c2_mf_k128") if wl == "netflix" else None
+    model = mb.seeded_model(nu, nv, k, g["model_seed"] if g else 20261018)  # the same on every rank
+
+    def restart():
+        w.ctx.set_factors(*model)
+        w.epochs_done = 0
+        epoch[0] = 0
 
     def step():
         epoch[0] += 1
@@ -139,6 +150,35 @@ def bench(args, wl, shape, rank, world, local, config):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
         return float(ms[0]), float(ms[1])
 
+    tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    ntrain = int(tot[0])
+
+    # ---- parity with the reference's own single-thread trajectory: same data, same seeded model ---------------
+    parity = None
+    if g and not args.no_parity:
+        restart()
+        ref = g["test_rmse"]
+        traj, cum_ms = [], []
+        for _ in range(len(ref) + 4):
+            ms, _ = timed(step, 1)
+            cum_ms.append((cum_ms[-1] if cum_ms else 0.0) + ms)
+            sse, n = w.global_sse(GB)
+            traj.append(float(np.sqrt(sse / max(n, 1))))
+            if len(traj) >= len(ref) and first_epoch_within(traj, ref[-1]):
+                break
+        reach = first_epoch_within(traj, ref[-1])
+        at = len(ref) - 1
+        parity = {"test_rmse": traj[at], "test_rmse_reference": ref[-1], "rmse_abs_diff": abs(traj[at] - ref[-1]),
+                  "rmse_max_abs_diff_over_epochs": max(abs(a - b) for a, b in zip(traj, ref)),
+                  "rmse_trajectory": traj, "rmse_reference_trajectory": ref, "epoch_ms": [b - a for a, b in zip([0.0] + cum_ms[:-1], cum_ms)],
+                  "epochs_to_rmse": reach, "seconds_to_rmse": cum_ms[reach - 1] * 1e-3 if reach else None,
+                  "rmse_target": "reference's tRMSE after epoch %d (%.6f) + %g" % (len(ref), ref[-1], RMSE_TOL),
+                  "first_epoch_ring_turns": w.first_epoch_rotations,
+                  "reference": "oracle/_ref/mf_ref --fly 1 on the same generated file from the same seeded model "
+                               "(tests/golden/fullsize/c2_mf_k128.json); seconds = device time of the epochs, max over ranks"}
+
+    restart()
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
@@ -147,13 +187,11 @@ def bench(args, wl, shape, rank, world, local, config):
     la = w.ctx.launch_count()
     total_ms, _ = timed(step, args.steps)
     launches_resident = w.ctx.launch_count() - la
-    tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
-    dist.all_reduce(tot)
-    ntrain = int(tot[0])
     value = ntrain * args.steps / (total_ms * 1e-3)
+    timeline = [float(x) for x in w.ctx.dsgd_timeline(world * w.halves)]
 
-    # end to end: every step re-sends this rank's rating tiles from pinned host memory and reads
-    # the global test SSE back
+    # end to end: every step re-sends this rank's rating tiles from pinned host memory (compact 3-byte records
+    # when the data allow) and reads the global test SSE back
     for b in w.cells:
         b.pin()
     sse_host = []
@@ -166,12 +204,12 @@ def bench(args, wl, shape, rank, world, local, config):
 
     step_e2e()
     lb = w.ctx.launch_count()
+    hb = w.ctx.h2d_bytes()
     e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps)
     launches_e2e = w.ctx.launch_count() - lb
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed legs
     e2e_ms = max(e2e_dev_ms, e2e_wall_ms)
-    h2d = sum(b.nratings * 8 + b.nruns * 8 + 4 for b in w.cells)
-    h2d_t = torch.tensor([h2d], dtype=torch.int64, device="cuda")
+    h2d_t = torch.tensor([(w.ctx.h2d_bytes() - hb) // args.steps], dtype=torch.int64, device="cuda")
     dist.all_reduce(h2d_t)
     sse, n = sse_host[-1]
     launches = launches_resident + launches_e2e  # this rank's kernels inside the two timed regions
@@ -185,20 +223,30 @@ def bench(args, wl, shape, rank, world, local, config):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "launch": shape,
-                         "note": "per GPU, whole DSGD epoch (P cell kernels + P ring shifts), algorithmic bytes"},
+                         "note": "per GPU, whole DSGD epoch (P cell kernels + P ring shifts), algorithmic bytes; the cell kernels "
+                                 "are bound by the L2 atomic path like the single-GPU kernel (see the N=1 line), by the share "
+                                 "of the hottest item inside a cell (P times the file's) and by the length of the run pieces"},
             "cpu_baseline": None,
             "e2e": {"value": ntrain * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d_t[0]), "d2h_bytes_per_step": 16 * world,
                     "ms_per_step": e2e_ms / args.steps,
-                    "what": "per rank: H2D of its cell tiles + mfb_dsgd_epoch + gathered test SSE, max over ranks"},
+                    "what": "per rank: H2D of its cell tiles (3-byte records when the data allow) + mfb_dsgd_epoch_ex + gathered "
+                            "test SSE, max over ranks"},
             "clocks": clocks, "gpu_launches": launches,
             "gpu_launches_detail": {"per": "rank 0", "resident_leg": launches_resident, "e2e_leg": launches_e2e,
                                     "whole_run": w.ctx.launch_count() - launches0},
             "placement": dict(zip(("calibration_ms", "kept"), w.ctx.placement_report())),
-            "test_rmse": float(np.sqrt(sse / max(n, 1))),
+            "test_rmse": parity["test_rmse"] if parity else float(np.sqrt(sse / max(n, 1))),
+            "test_rmse_reference": parity["test_rmse_reference"] if parity else None,
+            "rmse_abs_diff": parity["rmse_abs_diff"] if parity else None,
+            "parity": parity,
+            "test_rmse_after_all_legs": float(np.sqrt(sse / max(n, 1))),
             "epochs_run": epoch[0], "train_ratings": ntrain, "gen_s": round(gen_s, 2),
-            "dsgd": {"cells_per_rank": world, "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
-                     "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch"},
+            "dsgd": {"cells_per_rank": world * w.halves, "pieces_per_block": w.halves,
+                     "first_epoch_ring_turns": w.first_epoch_rotations,
+                     "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
+                     "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch on a communication stream",
+                     "rank0_timeline_ms_wait_kernel": timeline},
         }
         print(json.dumps(line))
     w.close()

@@ -69,12 +69,11 @@ void mfb_destroy(mfb_ctx* ctx);
 /* run all work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int mfb_set_stream(mfb_ctx* ctx, void* cuda_stream);
 int mfb_sync(mfb_ctx* ctx);
-/* tuning knobs (DESIGN.md "concurrency bounds"): "row_concurrency" (default 32: bound on the stale
+/* tuning knobs (DESIGN.md "concurrency bounds"): "row_concurrency" (default 16: bound on the stale
  * updates of the hottest item row in flight at once, at eta = 0.02), "eta_scaling" (1: that bound
  * widens with 0.02/eta; 2: the run bound too; 0: off), "run_fraction_ppm" (default 3500: user-runs in
- * flight / user-runs of the file; applies during the first "run_bound_epochs" (default 1) epochs after the
- * factors were set - "model_age" is that epoch count, kept by the library, settable by hosts that load a
- * trained model or drive epochs slice by slice), "max_groups" (explicit number of runs in flight), "kernel"
+ * flight / user-runs of the file; "run_bound_epochs" = n lifts it n epochs after the factors were set - default:
+ * never, see mfb_internal.h - and "model_age" is that epoch count, kept by the library, settable by hosts), "max_groups" (explicit number of runs in flight), "kernel"
  * (0 = choose, 1 = generic warp per run, 3 = sub-warp stream, 4 = burst), "ring" (1..4), "throttle",
  * "ctas_per_sm", "threads", "memopt" */
 int mfb_set_option(mfb_ctx* ctx, const char* name, int value);

@@ -40,6 +40,12 @@ float mfo_seteta_cutoff(float eta0, int round, float gam, float mineta) {
 }
 
 void mfo_srand(unsigned seed) { srand(seed); }
+/* n draws of the reference's validation index, `rand() % nvalid` (admf.h:82), in the order the filter makes them
+ * (one per user of the file) */
+void mfo_rand_draws(int64_t n, int64_t nvalid, int32_t* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = (int32_t)((size_t)rand() % (size_t)nvalid);
+}
+
 
 /* =============================== blocks.proto wire format =================================== */
 static int get_varint(const uint8_t** pp, const uint8_t* end, uint64_t* out) {

@@ -153,6 +153,8 @@ void mfo_shuffle_valid(int64_t n, int32_t* u, int32_t* v, float* r);
 void mfo_admf_epoch(mfo_model* m, const mfo_data* d, mfo_ad_state* st, float gb);
 
 void mfo_srand(unsigned seed);
+/* n times rand() % nvalid (admf.h:82) */
+void mfo_rand_draws(int64_t n, int64_t nvalid, int32_t* out);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,7 @@ def oracle():
         L.mfo_admf_epoch.argtypes = [C.POINTER(MfoModel), C.POINTER(MfoData),
                                      C.POINTER(MfoAdState), C.c_float]
         L.mfo_srand.argtypes = [C.c_uint]
+        L.mfo_rand_draws.argtypes = [C.c_int64, C.c_int64, i32p]
         L.mfo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint32)]
         L.mfo_philox_normal4.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int32, C.c_int64,

@@ -31,7 +31,9 @@ def test_reference_arm_prints_one_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
     assert d["metric"] == "rating updates/sec per epoch" and d["unit"] == "updates/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32"
-    assert d["config"]["workload"].startswith("ml1m-shaped") and d["config"]["k"] == 32
+    # a sampled run says so in its own config (it does not borrow the label of the arm it stands beside)
+    assert d["config"]["workload"].startswith("first ") and "ml1m-shaped" in d["config"]["workload"] and d["config"]["k"] == 32
+    assert 200000 <= d["config"]["ratings"] == d["train_ratings"] < 300000
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "ratings" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -47,6 +49,21 @@ def test_reference_arm_under_torchrun_only_rank_zero_prints():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["parallelism"] == "dsgd2"
+
+
+@needs_ref
+def test_reference_arm_runs_the_whole_file_by_default_and_loads_no_product_library():
+    """no --cpu-sample: the whole file of the workload, labelled as such; the arm's own process never maps
+    libmf_b200.so (the data come from the getdata binary, a separate process)"""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'ml1m', '--steps', '1', '--warmup', '1'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "import os; maps = open('/proc/self/maps').read(); assert 'libmf_b200' not in maps, 'product library mapped'"
+            % os.path.join(ROOT, "bench.py"))
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["config"]["workload"].startswith("ml1m-shaped") and d["config"]["ratings"] == 1_000_000
+    assert 850_000 < d["train_ratings"] < 950_000 and "all " in d["cpu_baseline"]["sample"]
 
 
 def test_gpu_arm_fails_loudly_without_a_device():

@@ -116,3 +116,17 @@ def test_resumed_run_continues_with_the_next_rounds_step_size(files):
     os.unlink(d + "/half_2.state")
     restarted = mf("--iter", 2, "--model", d + "/half_2")
     assert restarted != whole[2:] and len(restarted) == 2
+
+
+def test_out_of_core_driver_prints_the_resident_drivers_lines(files):
+    """MF_TILE_RATINGS: the `mf` driver trains straight from the file (two small device tile buffers), as the reference
+    does; in the ordered schedule the printed test RMSE is the resident run's, digit for digit."""
+    d, tp, sp = files
+    common = [MF, "--alg", "mf", "--train", tp, "--test", sp, "--nu", NU, "--nv", NV, "--dim", DIM, "--fly", 1, "--iter", 3,
+              "--eta", 3e-2, "--lambda", 5e-3, "--gam", 1.0, "--bias", GB]
+    outs = []
+    for env in ({}, {"MF_TILE_RATINGS": "1024"}):
+        out = subprocess.run([str(a) for a in common], capture_output=True, text=True, env=dict(os.environ, MF_SEED="5", **env))
+        assert out.returncode == 0, out.stderr
+        outs.append([x.split("tRMSE=")[1] for x in out.stdout.splitlines() if "tRMSE=" in x])
+    assert len(outs[0]) == 3 and outs[0] == outs[1]

@@ -70,8 +70,8 @@ def test_multi_rank_ring_is_bit_exact_with_the_oracle_walking_the_same_schedule(
     """The real thing, on every visible GPU pair: one process per GPU, ordered cells, half-block shifts over
     NCCL overlapped with the other half's kernel, three ring turns in epoch 1 - the factors of every rank must
     equal the CPU oracle walking the same schedule of pieces, bit for bit (tools/dsgd_check.py exits 1 if not)."""
-    import torch
-    n = torch.cuda.device_count()
+    out = subprocess.run([sys.executable, "-c", "import torch; print(torch.cuda.device_count())"], capture_output=True, text=True)
+    n = int(out.stdout.strip() or 0)
     if n < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     world = 4 if n >= 4 else 2

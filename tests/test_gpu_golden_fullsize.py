@@ -1,0 +1,195 @@
+"""PARITY at the BASELINE.json config sizes (Netflix shape, 480,189 x 17,770, 100 M ratings) against trajectories
+of the REFERENCE ITSELF committed under tests/golden/fullsize/ (generator: tests/golden/make_fullsize_golden.py -
+the reference's own main() / filters compiled where they lie, same generated files, same seeded model):
+
+  C2  mf k=128, production schedule on one GPU            |tRMSE - reference| <= 1e-3 after epoch 10
+  C2  the P = 8 DSGD schedule (walked by one GPU)          same bound - with the 16 ring turns of epoch 1
+  C3  dpmf eps=0 (pure SGLD) k=128                         statistical: different noise streams (table vs Philox)
+  C4  dpmf eps=1 k=64; admf k=64 (lambda trajectory)
+
+Tolerance: BASELINE.json north_star's 1e-3 absolute on the final test RMSE.  How tight that is: the reference's
+own `--fly 8` runs end within 1e-5 of its `--fly 1` run (c2_mf_k128_fly8.json), and two noise seeds of its SGLD run
+end 5e-4 apart (c3_sgld_k128_seed1/2.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mfb200 as mb
+import mfb_dsgd
+import oraclelib as ol
+from oraclelib import _p, f32p, i32p
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+NU, NV, NNZ = 480_189, 17_770, 100_000_000
+TOL = 1e-3
+
+
+def gold(name):
+    return json.load(open(os.path.join(HERE, "golden", "fullsize", name + ".json")))
+
+
+@pytest.fixture(scope="module")
+def data():
+    tr, te, _ = mb.generate(mb.gen_params(NU, NV, NNZ))
+    return tr, te
+
+
+def test_c2_production_schedule_follows_the_reference_trajectory(data):
+    tr, te = data
+    g = gold("c2_mf_k128")
+    assert g["shape"] == {"nu": NU, "nv": NV, "nnz": NNZ}
+    c = mb.Context(NU, NV, 128)
+    c.set_factors(*mb.seeded_model(NU, NV, 128, g["model_seed"]))
+    dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+    traj = []
+    for ep in range(1, len(g["test_rmse"]) + 1):
+        c.sgd_epoch(dtr, mb.seteta(g["eta0"], ep, g["gam"]), g["lambda"], g["gb"], mb.MODE_ATOMIC)
+        traj.append(c.rmse(dte, g["gb"]))
+    c.close()
+    d = [a - b for a, b in zip(traj, g["test_rmse"])]
+    print("reference", g["test_rmse"])
+    print("b200     ", [round(x, 6) for x in traj])
+    print("diff     ", ["%+.5f" % x for x in d])
+    assert abs(d[-1]) <= TOL
+    assert max(abs(x) for x in d[1:]) <= 2 * TOL  # the whole trajectory from epoch 2 on (epoch 1: <= 3e-3, the run bound)
+    assert abs(d[0]) <= 3e-3
+    # the reference's own parallel runs (--fly 8) on this file: the scale of its run-to-run spread
+    fly = gold("c2_mf_k128_fly8")
+    assert max(abs(r["test_rmse"][-1] - g["test_rmse"][-1]) for r in fly["runs"]) <= 1e-4
+
+
+def test_c2_dsgd_schedule_of_8_ranks_follows_the_reference_trajectory():
+    """What 8 GPUs compute, walked by one (cells of one sub-epoch share no user and no item, so any serialisation is
+    the parallel result up to intra-cell Hogwild effects; the ring itself is checked bit for bit by the multi-rank
+    test in test_gpu_dsgd.py): 16 ring turns in epoch 1, one per epoch afterwards.  With one turn in every epoch the
+    same run ends +0.0275 above the reference (gpurun_out/r2_exp_fullsize.log)."""
+    P, g = 8, gold("c2_mf_k128")
+    c = mb.Context(NU, NV, 128)
+    c.set_option("placement_trials", 0)
+    cells, tests = [], []
+    bounds = mfb_dsgd.item_bounds(NV, P)
+    for p in range(P):
+        u0, u1 = mfb_dsgd.user_range(NU, p, P)
+        trp, tep, _ = mb.generate(mb.gen_params(NU, NV, NNZ, user_begin=u0, user_end=u1))
+        cells.append([c.dataset_from_blocks(b) for b in trp.split_by_item(bounds)])
+        tests.append(c.dataset_from_blocks(tep))
+    c.set_factors(*mb.seeded_model(NU, NV, 128, g["model_seed"]))
+    traj = []
+    for ep in range(1, len(g["test_rmse"]) + 1):
+        eta = mb.seteta(g["eta0"], ep, g["gam"])
+        rot = mfb_dsgd.FIRST_EPOCH_ROTATIONS if ep == 1 else 1
+        c.set_option("model_age", ep - 1)
+        for scheds in zip(*[mfb_dsgd.piece_schedule(p, P, 1, rot) for p in range(P)]):
+            for p, (turn, j) in enumerate(scheds):
+                k0, k1 = mfb_dsgd.turn_blocks(c.num_blocks(cells[p][j]), turn, rot)
+                c.sgd_epoch_blocks(cells[p][j], k0, k1, eta, g["lambda"], g["gb"], mb.MODE_ATOMIC)
+        sse = n = 0
+        for d in tests:
+            a, b = c.sse(d, g["gb"])
+            sse, n = sse + a, n + b
+        traj.append(float(np.sqrt(sse / n)))
+    c.close()
+    print("reference", g["test_rmse"])
+    print("dsgd P=8 ", [round(x, 6) for x in traj])
+    assert abs(traj[-1] - g["test_rmse"][-1]) <= TOL
+
+
+def run_dpmf(tr, te, g, k):
+    """run(DPMF&) (main.cc:55-75) + finish_round (model.cc:299-310) through the C ABI; the Gibbs draws are host
+    code (numpy's gamma: at these counts the posteriors are sharp, rel. sd < 2e-3)."""
+    c = mb.Context(NU, NV, k)
+    c.set_factors(*mb.seeded_model(NU, NV, k, g["model_seed"]))
+    c.enable(2)
+    d, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+    ntrain = c.dp_weights(d)
+    assert ntrain == g["ntrain"]
+    bound = mb.lib().mfb_dp_bound(g["epsilon"], 0, NV)
+    assert abs(bound - g["bound"]) <= 1e-6 * g["bound"]
+    lam_u, lam_v = np.full(k, 1e2, np.float32), np.full(k, 1e2, np.float32)
+    lam_r, lam_ub, lam_vb = 1.0, 1e2, 1e2
+    rng = np.random.default_rng(7)
+    a, b = g["hyper_a"], g["hyper_b"]
+
+    def gibbs(sum_sq, count):
+        return float(rng.gamma(a + 0.5 * count, 1.0 / (b + 0.5 * sum_sq)))
+
+    test_rmse, train_rmse, lr = [], [], []
+    for rnd in range(1, len(g["test_rmse"]) + 1):
+        eta = mb.lib().mfb_seteta_cutoff(np.float32(g["eta0"]), rnd, g["gam"], g["mineta"])
+        assert abs(eta - g["eta"][rnd - 1]) <= 1e-6 * eta
+        c.upload(mb.LAMBDA_U, lam_u)
+        c.upload(mb.LAMBDA_V, lam_v)
+        p = mb.SgldParams(eta, np.float32(g["temp"]), bound, ntrain, lam_r, lam_ub, lam_vb, 2026, rnd, 0, 0)
+        c.sgld_epoch(d, p, g["gb"], mb.MODE_HOGWILD)
+        c.sgld_flush_noise(d, p)
+        s_tr, n_tr = c.sse(d, g["gb"])
+        train_rmse.append(float(np.sqrt(s_tr / n_tr)))
+        test_rmse.append(c.rmse(dte, g["gb"]))
+        nu_, nv_, bu2, bv2 = c.col_sqnorms()
+        lam_r, lam_ub, lam_vb = gibbs(s_tr, ntrain), gibbs(bu2, NU), gibbs(bv2, NV)
+        lam_u = np.array([gibbs(x, NU) for x in nu_], np.float32)
+        lam_v = np.array([gibbs(x, NV) for x in nv_], np.float32)
+        lr.append(lam_r)
+    c.close()
+    return test_rmse, train_rmse, lr
+
+
+@pytest.mark.parametrize("name,k", [("c3_sgld_k128_seed1", 128), ("c4_dpmf_k64_eps1_seed1", 64)])
+def test_c3_c4_dpmf_follows_the_reference_trajectory(data, name, k):
+    tr, te = data
+    g = gold(name)
+    test_rmse, train_rmse, lam_r = run_dpmf(tr, te, g, k)
+    print("reference tRMSE", g["test_rmse"])
+    print("b200      tRMSE", [round(x, 5) for x in test_rmse])
+    print("reference RMSE ", g["train_rmse"])
+    print("b200      RMSE ", [round(x, 5) for x in train_rmse])
+    print("lambda_r ref/b200", g["lambda_r"][-1], lam_r[-1])
+    assert all(np.isfinite(test_rmse))
+    # every round of the posterior-sample trajectory, test and train, and the sampled residual precision
+    assert max(abs(a - b) for a, b in zip(test_rmse, g["test_rmse"])) <= 2 * TOL
+    assert abs(test_rmse[-1] - g["test_rmse"][-1]) <= TOL
+    assert max(abs(a - b) for a, b in zip(train_rmse, g["train_rmse"])) <= 2 * TOL
+    assert abs(lam_r[-1] - g["lambda_r"][-1]) <= 0.02 * g["lambda_r"][-1]
+
+
+def test_c4_admf_follows_the_reference_trajectory_and_lambdas():
+    g = gold("c4_admf_k64")
+    k = 64
+    tr, te, va = mb.generate(mb.gen_params(NU, NV, NNZ, valid_frac=0.01))
+    c = mb.Context(NU, NV, k)
+    c.set_factors(*mb.seeded_model(NU, NV, k, g["model_seed"]))
+    c.enable(1)
+    c.snapshot_old()
+    d, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
+    # the reference's own rand() stream (srand(5), as the golden run): the shuffle of the validation list
+    # (model.cc:413) and then one rand() % |valid| per user-run of the file (admf.h:82)
+    vu = np.repeat(va.run_uid, np.diff(va.run_off)).astype(np.int32)
+    vv, vr = np.array(va.vid, np.int32), np.array(va.rating, np.float32)
+    assert len(vu) == g["nvalid"]
+    L = ol.oracle()
+    L.mfo_srand(g["srand"])
+    L.mfo_shuffle_valid(len(vu), _p(vu, i32p), _p(vv, i32p), _p(vr, f32p))
+    c.admf_set_validation(vu, vv, vr)
+    c.admf_set_lams([g["lambda"]] * 4)
+    traj, lams = [], []
+    for ep in range(1, len(g["test_rmse"]) + 1):
+        draws = np.zeros(tr.nruns, np.int32)
+        L.mfo_rand_draws(tr.nruns, len(vu), _p(draws, i32p))
+        c.admf_set_draws(draws)
+        c.admf_epoch(d, mb.seteta(g["eta0"], ep, g["gam"]), mb.seteta(g["eta_reg0"], ep, g["gam"]), 0, g["gb"], mb.MODE_ATOMIC)
+        traj.append(c.rmse(dte, g["gb"]))
+        lams.append([float(x) for x in c.admf_get_lams()])
+    c.close()
+    print("reference tRMSE", g["test_rmse"])
+    print("b200      tRMSE", [round(x, 5) for x in traj])
+    print("reference lams ", g["lams"][-1])
+    print("b200      lams ", lams[-1])
+    assert abs(traj[-1] - g["test_rmse"][-1]) <= TOL
+    assert max(abs(a - b) for a, b in zip(traj[1:], g["test_rmse"][1:])) <= 2 * TOL
+    # the four regularisers at the end of every epoch (same validation draws, parallel order of the updates)
+    got, want = np.array(lams), np.array(g["lams"])
+    assert np.abs(got[-1] - want[-1]).max() <= 0.05 * np.abs(want[-1]).max()
+    assert (np.abs(got - want) <= 0.1 * np.abs(want) + 2e-4).all()
