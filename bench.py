@@ -498,11 +498,17 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
         peak = measured_peak()[0]
         ach = try_.nratings * bytes_per_update(yk) / (kms * 1e-3) / 1e9
         prof, prof_src = profiled("sgd_stream_yahoo")
+        traffic = prof.get("dram_traffic_bytes") if prof else None
         return {"workload": workload_config("yahoo", 1)["workload"] + " on ONE GPU (the item matrix, 320 MB, does not fit the L2)",
                 "ms_per_epoch": kms, "updates_per_s": try_.nratings / kms * 1e3, "launch": shape,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": prof.get("dram_traffic_bytes") if prof else None, "traffic_source": prof_src,
-                             "note": "algorithmic bytes; user rows stay in registers for a run, so DRAM traffic is lower"},
+                             "traffic": traffic, "traffic_source": prof_src,
+                             "dram_gbs": traffic / (kms * 1e-3) / 1e9 if traffic else None,
+                             "dram_frac_of_peak": traffic / (kms * 1e-3) / 1e9 / peak if traffic else None,
+                             "note": "achieved = algorithmic bytes (12 + 16k per update); dram_gbs = what ncu saw move (user rows stay "
+                                     "in registers for a run, part of the 320 MB item matrix is served by the 126 MB L2): this "
+                                     "shape reads and writes DRAM at a fifth of its bandwidth - the L2 atomic path binds here too "
+                                     "(busiest slice's atomic unit 76 % busy, profiles/r2_sgd_stream_yahoo.md)"},
                 "test_rmse_after_%d_epochs" % len(ms): rm}
 
     if args.yahoo:

@@ -828,7 +828,9 @@ int mfb_sgd_epoch_blocks(mfb_ctx* h, int ds, int64_t block_begin, int64_t block_
   MFB_CUDA(cudaSetDevice(c->device));
   begin_timing(c);
   const int64_t r0 = d->h_block_off[block_begin], r1 = d->h_block_off[block_end];
+  c->planes_allowed = true;  // (this launch has the item matrix to itself)
   int rc = r1 > r0 ? launch_sgd(c, d, eta, lambda, gb, mode, r0, r1) : MFB_OK;
+  c->planes_allowed = false;
   end_timing(c);
   return rc;
 }

@@ -191,5 +191,8 @@ def test_c4_admf_follows_the_reference_trajectory_and_lambdas():
     assert max(abs(a - b) for a, b in zip(traj[1:], g["test_rmse"][1:])) <= 2 * TOL
     # the four regularisers at the end of every epoch (same validation draws, parallel order of the updates)
     got, want = np.array(lams), np.array(g["lams"])
-    assert np.abs(got[-1] - want[-1]).max() <= 0.05 * np.abs(want[-1]).max()
-    assert (np.abs(got - want) <= 0.1 * np.abs(want) + 2e-4).all()
+    assert (np.abs(got[-1] - want[-1]) <= 0.03 * np.abs(want[-1])).all()       # every regulariser at the end: 3 %
+    # the trajectories: the bias regularisers (0.38 -> 0.45) to 5 % in every epoch; the factor regularisers start at
+    # 5e-3, fall to ~1e-3 in epoch 1 (clamped at zero on the way: model.h:94) and recover to 3e-3: absolute 1e-3
+    assert (np.abs(got[:, 2:] - want[:, 2:]) <= 0.05 * np.abs(want[:, 2:])).all()
+    assert np.abs(got[:, :2] - want[:, :2]).max() <= 1e-3

@@ -45,9 +45,10 @@ if "T" in parts:
         P, n0, tr.nruns, [b.nruns for b in cells], np.mean(np.concatenate(lens)), max(int(l.max()) for l in lens),
         ["%.3f" % (np.bincount(np.asarray(b.vid)).max() / b.nratings) for b in cells]), flush=True)
     eta = 0.004
-    for kern in (3, 4):
-        for age, rc in ((0, 32), (5, 8), (5, 16), (5, 32), (5, 64)):
+    for kern, planes in ((3, 0), (3, 1), (4, 0)):
+        for age, rc in ((5, 16), (5, 32), (5, 64)):
             c.set_option("kernel", kern); c.set_option("model_age", age); c.set_option("row_concurrency", rc)
+            c.set_option("phi_planes", planes)
             for rep in range(2):
                 per = []
                 for d in ds:
@@ -55,8 +56,8 @@ if "T" in parts:
                 shape = c.last_launch()
                 c.sgd_epoch_blocks(dcat, 0, c.num_blocks(dcat), eta, LAM, GB, mb.MODE_ATOMIC); one = c.last_kernel_ms()
                 c.sgd_epoch_blocks(dall, 0, c.num_blocks(dall), eta, LAM, GB, mb.MODE_ATOMIC); whole = c.last_kernel_ms()
-            print("T kernel %d model_age %d rc %2d: 8 cell launches %.2f ms (%s) | one launch over the same cells %.2f ms | the shard in file "
-                  "order (whole runs) %.2f ms | %s" % (kern, age, rc, sum(per), " ".join("%.2f" % x for x in per), one, whole, shape), flush=True)
+            print("T kernel %d planes %d rc %2d: 8 cell launches %.2f ms (%s) | one launch over the same cells %.2f ms | the shard in file "
+                  "order (whole runs) %.2f ms | %s" % (kern, planes, rc, sum(per), " ".join("%.2f" % x for x in per), one, whole, shape), flush=True)
     c.close()
     del tr, te, cells, cat
 
