@@ -720,6 +720,7 @@ int mfb_dataset_finalize(mfb_ctx* h, int ds) {
     std::vector<int32_t> last_u(c->nu, 0), last_v(c->nv, 0), run_uc(d->nruns, 0), vc(d->nratings, 0);
     d->h_ucount.assign(c->nu, 0);
     d->h_vcount.assign(c->nv, 0);
+    // users: one step per run (runs are few)
     for (int64_t r = 0; r < d->nruns; r++) {
       const int32_t u = d->h_run_uid[r];
       const int32_t lo = d->h_run_off[r], hi = d->h_run_off[r + 1];
@@ -727,11 +728,34 @@ int mfb_dataset_finalize(mfb_ctx* h, int ds) {
       run_uc[r] = lo - last_u[u];          // dpmf.h:65: uc = gc - gcountu[uid], gc == record index
       last_u[u] = hi - 1;                  // dpmf.h:66
       d->h_ucount[u] += hi - lo;
-      for (int32_t t = lo; t < hi; t++) {
-        const int32_t v = d->h_vid[t];
-        vc[t] = t - last_v[v];             // dpmf.h:63
-        last_v[v] = t;
-        d->h_vcount[v]++;
+    }
+    // items: vc[t] = t - (previous record of the same item), dpmf.h:63.  The records are cut into one range per
+    // thread; a range resolves every record but the first of each item inside itself, and a serial sweep over the
+    // ranges (nv steps each) hands the first ones the last occurrence in the ranges before.
+    const int64_t n = d->nratings;
+    const int64_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const int64_t parts = std::max<int64_t>(1, std::min<int64_t>(hw, n / (1 << 16)));
+    std::vector<std::vector<int32_t>> first((size_t)parts), last((size_t)parts), count((size_t)parts);
+    const int32_t* v = d->h_vid.data();
+    parallel_ranges(n, [&](int t, int64_t b, int64_t e) {
+      std::vector<int32_t>&f = first[t], &l = last[t], &k = count[t];
+      f.assign(c->nv, -1);
+      l.assign(c->nv, -1);
+      k.assign(c->nv, 0);
+      for (int64_t i = b; i < e; i++) {
+        const int32_t it = v[i];
+        if (l[it] >= 0) vc[i] = (int32_t)(i - l[it]);
+        else f[it] = (int32_t)i;
+        l[it] = (int32_t)i;
+        k[it]++;
+      }
+    });
+    for (int64_t t = 0; t < parts; t++) {
+      if (first[t].empty()) continue;  // (parallel_ranges may use fewer parts than asked for)
+      for (int32_t it = 0; it < c->nv; it++) {
+        if (first[t][it] >= 0) vc[first[t][it]] = first[t][it] - last_v[it];  // (gcountv starts at 0, model.cc:235/326)
+        if (last[t][it] >= 0) last_v[it] = last[t][it];
+        d->h_vcount[it] += count[t][it];
       }
     }
     if ((rc = to_device(c, run_uc, &d->d_uc))) return rc;

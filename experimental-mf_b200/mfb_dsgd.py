@@ -154,6 +154,11 @@ def bench(args, wl, shape, rank, world, local, config):
     dist.all_reduce(tot)
     ntrain = int(tot[0])
 
+    # one epoch at eta = 0 (the identity on the model) before anything is timed: NCCL sets its connections up on the
+    # first send/recv (~0.8 s) and the library searches the placement of the item matrix on the first epoch
+    w.ctx.dsgd_epoch(w.cell_ds, w.bounds, 0.0, 0.0, GB, mode, w.halves, 1)
+    torch.cuda.synchronize()
+
     # ---- parity with the reference's own single-thread trajectory: same data, same seeded model ---------------
     parity = None
     if g and not args.no_parity:

@@ -28,8 +28,8 @@ unique_id = bytes(uid.cpu().numpy().tobytes())
 u0, u1 = mfb_dsgd.user_range(NU, rank, world)
 tr, te, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.1, user_begin=u0, user_end=u1))
 m = ol.Model(NU, NV, DIM, seed=11)
-th, ph = m.dense()
-bu0, bv0 = m.bu.copy(), m.bv.copy()  # rank 0 trains `m` in place below
+th, ph = [x.copy() for x in m.dense()]  # (views when dim == stride) rank 0 trains `m` in place below
+bu0, bv0 = m.bu.copy(), m.bv.copy()
 H, R1 = int(os.environ.get("HALVES", "2")), int(os.environ.get("ROTATIONS", "3"))
 w = mfb_dsgd.DsgdWorker(NU, NV, DIM, rank, world, local, tr, te, unique_id, halves=H, first_epoch_rotations=R1)
 w.ctx.set_factors(th, ph, m.bu, m.bv)
