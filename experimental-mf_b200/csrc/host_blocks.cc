@@ -126,8 +126,9 @@ int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bou
 //   merge_users: one run per user - the user's runs concatenated in file order, users in the order of their first
 //     run.  (A DSGD cell holds, for each user, the pieces of `split` runs of the source file; merged, the factor row
 //     is read and written once per cell instead of once per piece.)
-//   longest_first: runs in descending order of length (stable) - longest-processing-time-first scheduling: a launch
-//     ends when its longest run still in flight ends, and a run is a sequential chain.
+//   longest_first: 1 = runs in descending order of length (stable) - longest-processing-time-first scheduling: a launch
+//     ends when its longest run still in flight ends, and a run is a sequential chain; N > 1 = only the runs of N
+//     records or more move to the front, the others keep their order.
 // `users_per_block` runs per Block.
 int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, int users_per_block, mfb_blocks** out) {
   MFB_REQUIRE(b && out && users_per_block >= 1, "bad argument");
@@ -165,8 +166,16 @@ int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, 
   const int64_t ng = (int64_t)g_uid.size();
   std::vector<int64_t> order((size_t)ng);
   for (int64_t i = 0; i < ng; i++) order[i] = i;
-  if (longest_first)
+  if (longest_first == 1) {
     std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return g_len[x] > g_len[y]; });
+  } else if (longest_first > 1) {
+    // only the runs of `longest_first` records or more move to the front (longest first); the others keep their order
+    const int64_t thr = longest_first;
+    std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return g_len[x] >= thr; });
+    int64_t nlong = 0;
+    while (nlong < ng && g_len[order[nlong]] >= thr) nlong++;
+    std::stable_sort(order.begin(), order.begin() + nlong, [&](int64_t x, int64_t y) { return g_len[x] > g_len[y]; });
+  }
   std::vector<int64_t> slot((size_t)ng), fill((size_t)ng, 0);
   mfb_blocks* o = blocks_new();  // run_off = block_off = {0}
   Dataset& m = o->d;

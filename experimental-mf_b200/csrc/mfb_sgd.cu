@@ -378,7 +378,7 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
       const int64_t runs = a.nruns - a.run_begin;
       const int64_t cap = (int64_t)c->sm_count * 64;  // more than either kernel holds: bounds only
       const double w_stream = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 1.0, eta), runs);
-      const double w_burst = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 8.0, eta), (runs + 31) / 32);
+      const double w_burst = (double)std::min<int64_t>(bounded_groups(c, cap, d->max_item_share, d->nruns, 4.0, eta), (runs + 31) / 32);
       const double stream = std::min(w_stream * c->rate_stream, 6.5e9), burst = std::min(w_burst * c->rate_burst, 5.8e9);
       if (burst > stream) c->use_kernel = 4;
     }

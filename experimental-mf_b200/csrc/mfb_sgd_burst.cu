@@ -418,7 +418,10 @@ int launch_burst_t(Context* c, const Dataset* d, const SgdArgs& a, int mode) {
   const int span_runs = c->opt_span_runs > 0 ? c->opt_span_runs : (d->nruns >= 400000 ? 32 : (d->nruns >= 100000 ? 16 : 8));
   int64_t warps = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4, std::max((nruns + span_runs - 1) / span_runs, 1));
   // a run holds the batch being computed and the D requested ones between gather and reduction
-  warps = bounded_groups(c, warps, d->max_item_share, d->nruns, (double)(D + 1) * B, a.eta);
+  // (The hot-row budget, row_concurrency = 16, was re-derived in round 2 for the STREAM kernel, whose wide launches
+  // are what went unstable.  This kernel was validated at what is now "32": round 1's 1-8 GPU runs and round 2's
+  // 8-rank schedule against the reference's trajectory.  Its run counts for half its rows so that it keeps that width.)
+  warps = bounded_groups(c, warps, d->max_item_share, d->nruns, 0.5 * (double)(D + 1) * B, a.eta);
   SgdArgs aa = a;
   aa.span_runs = span_runs;
   aa.big_spans = (int)std::max<int64_t>(0, (nruns - c->opt_tail_runs * warps) / span_runs);  // single runs at the end

@@ -253,8 +253,9 @@ int mfb_admf_epoch(mfb_ctx* ctx, int ds, float eta, float eta_reg, int loss, flo
 int mfb_blocks_split_by_item(const mfb_blocks* b, int nparts, const int32_t* bounds, mfb_blocks** out);
 /* one run per user (its runs concatenated in file order, users in order of first appearance) */
 int mfb_blocks_merge_runs(const mfb_blocks* b, int users_per_block, mfb_blocks** out);
-/* the general regrouping: merge_users != 0 as above; longest_first != 0: runs in descending order of length (a
- * launch ends when its longest run still in flight ends: longest-processing-time-first scheduling).  Changes the
+/* the general regrouping: merge_users != 0 as above; longest_first = 1: runs in descending order of length (a
+ * launch ends when its longest run still in flight ends: longest-processing-time-first scheduling); longest_first =
+ * N > 1: only the runs of N records or more move to the front, the others keep their order.  Changes the
  * order of updates: for epochs after the first, where the order no longer shows in the result. */
 int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, int users_per_block, mfb_blocks** out);
 int mfb_comm_unique_id(void* out128);

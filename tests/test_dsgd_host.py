@@ -143,3 +143,17 @@ def test_regroup_longest_first_keeps_every_record_and_sorts_runs():
         cu = np.repeat(cell.run_uid, np.diff(cell.run_off))
         if merge:
             np.testing.assert_array_equal(g.vid[:lens[0]], cell.vid[cu == u])
+
+
+def test_regroup_with_a_length_threshold_moves_only_the_long_runs():
+    nu, nv = 400, 90
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 20000, test_frac=0.0, users_per_block=50))
+    lens0 = np.diff(tr.run_off)
+    thr = int(np.sort(lens0)[-20])            # about 20 runs are "long"
+    g = tr.regroup(merge_users=False, longest_first=thr, users_per_block=50)
+    lens = np.diff(g.run_off)
+    nlong = int((lens0 >= thr).sum())
+    assert g.nruns == tr.nruns and g.nratings == tr.nratings
+    assert (lens[:nlong] >= thr).all() and (np.diff(lens[:nlong]) <= 0).all() and (lens[nlong:] < thr).all()
+    # the short runs keep their file order
+    np.testing.assert_array_equal(g.run_uid[nlong:], tr.run_uid[lens0 < thr])

@@ -134,8 +134,11 @@ def test_parallel_admf_tracks_serial_oracle_ml1m_shape():
         lw.append(np.array([st.lam_u, st.lam_v, st.lam_bu, st.lam_bv]))
     print("admf oracle  rmse", ["%.4f" % x for x in want], "lams", lw[-1])
     print("admf parallel rmse", ["%.4f" % x for x in got], "lams", lg[-1])
-    assert abs(got[-1] - want[-1]) <= 2e-3
-    np.testing.assert_allclose(lg[-1], lw[-1], rtol=0.1, atol=2e-4)
+    assert abs(got[-1] - want[-1]) <= 1e-3                     # north_star's bound (measured: 3e-4)
+    # the regularisers: the two bias ones (0.12) to 5 % (measured 0.1 % and 3 %); the two factor ones have fallen to
+    # ~1e-5, next to the clamp at zero (model.h:94), where only an absolute bound means anything (measured 1e-5)
+    np.testing.assert_allclose(lg[-1][2:], lw[-1][2:], rtol=0.05)
+    assert np.abs(lg[-1][:2] - lw[-1][:2]).max() <= 1e-4
     c.close()
 
 

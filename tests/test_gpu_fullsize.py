@@ -69,8 +69,8 @@ def test_stream_and_burst_kernels_agree_and_learn(data):
     print("stream", out[3], "burst", out[4])
     assert out[3][0] > out[3][1] > out[3][2] and out[3][2] < 0.62
     # the two kernels run with different numbers of user-runs in flight, which shows in the first epoch
-    #  and fades: 3e-3 after epoch 1, 1e-3 at the end
-    assert abs(out[3][0] - out[4][0]) <= 3e-3 and abs(out[3][-1] - out[4][-1]) <= 1e-3
+    #  and fades: measured 7.5e-4 after epoch 1, 2e-4 at the end
+    assert abs(out[3][0] - out[4][0]) <= 1.5e-3 and abs(out[3][-1] - out[4][-1]) <= 1e-3
 
 
 def test_sse_pass_equals_numpy_on_downloaded_factors(data):

@@ -206,5 +206,5 @@ def test_hogwild_sgld_rmse_close_to_serial_oracle():
     print("sgld oracle ", ["%.4f" % x for x in want])
     print("sgld hogwild", ["%.4f" % x for x in got])
     assert want[-1] < want[0]
-    assert abs(got[-1] - want[-1]) < 5e-3
+    assert abs(got[-1] - want[-1]) < 1e-3   # north_star's bound on the final test RMSE (measured: 1e-4)
     c.close()

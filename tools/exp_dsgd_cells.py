@@ -26,7 +26,8 @@ P = int(os.environ.get("P", "8"))
 R1 = int(os.environ.get("R1", "16"))
 TH, PH, BU, BV = mb.seeded_model(NU, NV, K, GOLD["model_seed"])
 # variant name -> (merge_users, longest_first) of the steady-state cells; None = the file-ordered cells
-VARIANTS = {"file": None, "lpt": (False, True), "merge": (True, False), "merge+lpt": (True, True)}
+VARIANTS = {"file": None, "lpt": (False, True), "merge": (True, False), "merge+lpt": (True, True),
+            "long64": (False, 64), "merge+long128": (True, 128), "merge+long256": (True, 256)}
 which = sys.argv[1:] or ["file", "merge+lpt"]
 
 c = mb.Context(NU, NV, K)
@@ -75,9 +76,13 @@ def walk(cellset, rot, eta, ranks=None):
 for v in which:
     c.set_factors(TH, PH, BU, BV)
     traj, ms, shp = [], [], None
+    nr_file = sum(c.num_runs(x) for row in cells["file"] for x in row)
+    nr_v = sum(c.num_runs(x) for row in cells[v] for x in row)
     for ep in range(1, EPOCHS + 1):
         c.set_option("model_age", ep - 1)   # (slices do not count as epochs: the host says how old the model is)
         cs = cells["file"] if ep == 1 else cells[v]
+        # the run bound is a number of users in flight: merged cells hold fewer, longer runs
+        c.set_option("run_fraction_ppm", 3500 if ep == 1 else int(3500 * nr_file / nr_v))
         m_, shp = walk(cs, R1 if ep == 1 else 1, mb.seteta(ETA0, ep, GAM))
         ms.append(m_)
         traj.append(rmse_all())
