@@ -640,31 +640,41 @@ def run_b200_arm(args, wl):
     final_rmse = float(np.sqrt(sse_host[-1] / te.nratings))
     tr.unpin()
 
-    # ---- leg 2b: out of core, straight from the protobuf file (decode on the host cores every epoch) -------
+    # ---- leg 2b: out of core, straight from the protobuf file: the raw bytes go to the GPU and are decoded there ----
     from_file = None
     if not args.no_file:
         tmp = scratch_dir()
         try:
             fp = tr.write(os.path.join(tmp, "train.bin"))
             fbytes = os.path.getsize(fp)
-            h2d1 = c.h2d_bytes()
-            secs = []
-            for _ in range(3):
-                epoch[0] += 1
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                n = c.sgd_epoch_from_file(fp, mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mode, args.tile)
-                s_ = c.sse(dte, GB)[0]
-                secs.append(time.perf_counter() - t0)
-                assert n == ntrain
-            best = min(secs[1:])
+
+            def file_epochs(reps):
+                secs, h0 = [], c.h2d_bytes()
+                for _ in range(reps):
+                    epoch[0] += 1
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    n = c.sgd_epoch_from_file(fp, mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mode, args.tile)
+                    s_ = c.sse(dte, GB)[0]
+                    secs.append(time.perf_counter() - t0)
+                    assert n == ntrain
+                return min(secs[1:]), (c.h2d_bytes() - h0) // reps, float(np.sqrt(s_ / te.nratings))
+
+            best, h2d_f, rmse_f = file_epochs(4)
+            c.set_option("file_decode", 0)
+            best_host, h2d_h, _ = file_epochs(2)
+            c.set_option("file_decode", 1)
             from_file = {"value": ntrain / best, "unit": UNIT, "ms_per_step": 1e3 * best, "file_bytes": fbytes,
-                         "h2d_bytes_per_step": (c.h2d_bytes() - h2d1) // 3, "tile_ratings": args.tile or (8 << 20),
-                         "device_tile_bytes": 2 * 8 * (args.tile or (8 << 20)), "host_cores": cores,
-                         "test_rmse": float(np.sqrt(s_ / te.nratings)),
-                         "what": "mfb_sgd_epoch_from_file: [u32][mf.Block] file (page cache) -> frames decoded by the host cores "
-                                 "into pinned chunks -> H2D -> kernel, two device tile buffers, nothing resident; + mfb_sse. "
-                                 "Wall clock, best of 2 after one warm-up; bound by the protobuf decode (file_bytes / time)"}
+                         "file_gb_per_s": fbytes / best / 1e9,
+                         "h2d_bytes_per_step": h2d_f, "tile_ratings": args.tile or (8 << 20), "host_cores": cores,
+                         "test_rmse": rmse_f,
+                         "host_decode": {"value": ntrain / best_host, "ms_per_step": 1e3 * best_host, "h2d_bytes_per_step": h2d_h,
+                                         "what": "option file_decode = 0: frames decoded by the host cores into pinned SoA chunks "
+                                                 "(the round's first version of this path)"},
+                         "what": "mfb_sgd_epoch_from_file: [u32][mf.Block] file (page cache) -> pread of whole frames into pinned "
+                                 "chunks, one jump per user on the host -> H2D of the RAW bytes -> varints / records decoded on the "
+                                 "GPU (mfb_wire_decode.cu) -> kernel; three slots of device buffers, nothing resident; + mfb_sse. "
+                                 "Wall clock, best of 3 after one warm-up"}
         except Exception as e:
             from_file = {"error": "%s: %s" % (type(e).__name__, e)}
         finally:

@@ -405,6 +405,7 @@ void mfb_destroy(mfb_ctx* h) {
   mfb_comm_destroy(h);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  free_file_pipe(c);
   for (auto& d : c->datasets) free_ds_device(&d);
   if (c->placement_arena) {  // phi/bv/plane scratch may live inside the arena of the placement search
     c->arr[MFB_PHI] = c->place0[0];
@@ -488,6 +489,9 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     c->opt_phi_planes = value;
   } else if (!strcmp(name, "two_streams")) {
     c->opt_two_streams = value != 0;
+  } else if (!strcmp(name, "file_decode")) {
+    MFB_REQUIRE(value == 0 || value == 1, "file_decode must be 0 (host cores) or 1 (device)");
+    c->opt_file_decode = value;
   } else if (!strcmp(name, "epoch_launches")) {
     MFB_REQUIRE(value >= 1 && value <= 4096, "epoch_launches out of range");
     c->opt_epoch_launches = value;

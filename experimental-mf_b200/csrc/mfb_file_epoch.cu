@@ -17,11 +17,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <future>
 #include <thread>
 #include <vector>
 
 #include "mfb_internal.h"
+#include "mfb_wire_decode.h"
 #include "proto_wire.h"
 
 namespace mfb {
@@ -159,15 +161,12 @@ int alloc_slot(Slot* s, int64_t cap_ratings, int64_t cap_runs) {
 
 using namespace mfb;
 
-extern "C" int mfb_sgd_epoch_from_file(mfb_ctx* h, const char* path, float eta, float lambda, float gb, int mode,
-                                       int64_t tile_ratings, int64_t* ratings_out) {
-  MFB_REQUIRE(h && path, "NULL argument");
-  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC, "bad mode %d", mode);
-  Context* c = &h->c;
-  MFB_CUDA(cudaSetDevice(c->device));
-  if (tile_ratings <= 0) tile_ratings = (int64_t)8 << 20;
-  tile_ratings = std::max<int64_t>(tile_ratings, 1024);
-  if (ratings_out) *ratings_out = 0;
+static int epoch_from_file_device(Context* c, const char* path, float eta, float lambda, float gb, int mode,
+                                  int64_t tile_ratings, int64_t* ratings_out);
+
+// the chunks decoded by the host cores (option file_decode = 0; the round-2 path, kept for comparison)
+static int epoch_from_file_host(Context* c, const char* path, float eta, float lambda, float gb, int mode,
+                                int64_t tile_ratings, int64_t* ratings_out) {
 
   const int fd = open(path, O_RDONLY);
   if (fd < 0) {
@@ -333,4 +332,457 @@ extern "C" int mfb_sgd_epoch_from_file(mfb_ctx* h, const char* path, float eta, 
     if (ratings_out) *ratings_out = total_ratings;
   }
   return rc;
+}
+
+// ---- the same epoch with the records decoded on the GPU (option file_decode = 1, the default) ---------------------
+//
+//   file (page cache) --pread by the host cores, frame by frame--> PINNED raw bytes of the chunk
+//        + the byte range of every serialized mf.User (one jump per user: the host only walks the top-level fields)
+//   --cudaMemcpyAsync (copy stream)--> device raw buffer --wire_{count,scan,decode}_kernel (copy stream)--> SoA tiles
+//   --epoch kernel (compute streams; consecutive chunks alternate over two of them at half the width each, so the
+//     tail of one launch overlaps the body of the next).
+// Three slots (pinned raw, device raw, device tiles) are kept in the context between epochs.  The host touches each
+// byte of the file once (the copy out of the page cache); the 100 M varints of a Netflix-sized file are read by the GPU.
+namespace mfb {
+namespace {
+
+struct FSlot {
+  uint8_t* h_raw = nullptr;
+  int32_t* h_span = nullptr;  // [2 * cap_runs] begin, end of every user inside the raw buffer
+  WireResult* h_res = nullptr;
+  uint8_t* d_raw = nullptr;
+  int32_t *d_span = nullptr, *d_run_uid = nullptr, *d_run_off = nullptr, *d_count = nullptr, *d_vid = nullptr;
+  float* d_rating = nullptr;
+  int32_t* d_hist = nullptr;
+  WireResult* d_res = nullptr;
+  size_t cap_bytes = 0;
+  int64_t cap_runs = 0, dev_cap_runs = 0, cap_ratings = 0;  // (span table on the host / run arrays on the device)
+  cudaEvent_t copied = nullptr, decode_begin = nullptr, decoded = nullptr, computed = nullptr;
+  bool copy_pending = false, decode_pending = false, compute_pending = false;
+  // the chunk the host stage left in the pinned buffers
+  int64_t nruns = 0;
+  size_t nbytes = 0;
+  bool ok = true;
+  size_t bad_frame = 0;
+};
+
+struct FilePipe {
+  FSlot slot[3];
+  // frame table of the file the pipe was last used on
+  std::string path;
+  int64_t size = -1, mtime_ns = -1;
+  std::vector<int64_t> frame_off;  // offset of every frame's payload; frame_off[i] - 4 is its header
+  std::vector<uint32_t> frame_size;
+  cudaEvent_t start = nullptr;
+  cudaStream_t decode_stream = nullptr;  // the decode kernels of chunk k run while the raw bytes of chunk k+1 are copied
+};
+
+void free_fslot(FSlot* s) {
+  cudaFreeHost(s->h_raw); cudaFreeHost(s->h_span); cudaFreeHost(s->h_res);
+  cudaFree(s->d_raw); cudaFree(s->d_span); cudaFree(s->d_run_uid); cudaFree(s->d_run_off); cudaFree(s->d_count);
+  cudaFree(s->d_vid); cudaFree(s->d_rating); cudaFree(s->d_hist); cudaFree(s->d_res);
+  if (s->copied) cudaEventDestroy(s->copied);
+  if (s->decoded) cudaEventDestroy(s->decoded);
+  if (s->decode_begin) cudaEventDestroy(s->decode_begin);
+  if (s->computed) cudaEventDestroy(s->computed);
+  *s = FSlot();
+}
+
+int ensure_bytes(FSlot* s, size_t bytes, int64_t ratings, int nv) {
+  if (!s->copied) {
+    MFB_CUDA(cudaEventCreateWithFlags(&s->copied, cudaEventDisableTiming));
+    MFB_CUDA(cudaEventCreate(&s->decoded));  // (timed: MFB_FILE_TIMING reports the decode kernels)
+    MFB_CUDA(cudaEventCreate(&s->decode_begin));
+    MFB_CUDA(cudaEventCreateWithFlags(&s->computed, cudaEventDisableTiming));
+    MFB_CUDA(cudaMallocHost(&s->h_res, sizeof(WireResult)));
+    MFB_CUDA(cudaMalloc(&s->d_res, sizeof(WireResult)));
+    MFB_CUDA(cudaMalloc(&s->d_hist, (size_t)std::max(nv, 1) * sizeof(int32_t)));
+  }
+  if (bytes > s->cap_bytes) {
+    if (s->decode_pending) MFB_CUDA(cudaEventSynchronize(s->decoded));
+    cudaFreeHost(s->h_raw); cudaFree(s->d_raw);
+    s->h_raw = nullptr; s->d_raw = nullptr; s->cap_bytes = 0;
+    MFB_CUDA(cudaMallocHost(&s->h_raw, bytes + 64));
+    MFB_CUDA(cudaMalloc(&s->d_raw, bytes + 64));  // the decoder reads whole 8-byte words, up to 16 bytes past the data
+    MFB_CUDA(cudaMemset(s->d_raw + bytes, 0, 64));
+    s->cap_bytes = bytes;
+  }
+  if (ratings > s->cap_ratings) {
+    if (s->compute_pending) MFB_CUDA(cudaEventSynchronize(s->computed));
+    cudaFree(s->d_vid); cudaFree(s->d_rating);
+    s->d_vid = nullptr; s->d_rating = nullptr; s->cap_ratings = 0;
+    MFB_CUDA(cudaMalloc(&s->d_vid, ratings * sizeof(int32_t)));
+    MFB_CUDA(cudaMalloc(&s->d_rating, ratings * sizeof(float)));
+    s->cap_ratings = ratings;
+  }
+  return MFB_OK;
+}
+
+// host side of the span table only (called from the worker thread of stage A: no device work pending on it there)
+int ensure_runs_host(FSlot* s, int64_t runs) {
+  if (runs <= s->cap_runs) return MFB_OK;
+  const int64_t cap = std::max<int64_t>(runs + runs / 4, 1 << 16);
+  cudaFreeHost(s->h_span);
+  s->h_span = nullptr;
+  s->cap_runs = 0;
+  MFB_CUDA(cudaMallocHost(&s->h_span, 2 * cap * sizeof(int32_t)));
+  // the device arrays follow in stage B (ensure_runs_device), on the thread that owns the streams
+  s->cap_runs = cap;
+  return MFB_OK;
+}
+int ensure_runs_device(FSlot* s) {
+  if (s->dev_cap_runs >= s->cap_runs) return MFB_OK;
+  if (s->compute_pending) MFB_CUDA(cudaEventSynchronize(s->computed));
+  cudaFree(s->d_span); cudaFree(s->d_run_uid); cudaFree(s->d_run_off); cudaFree(s->d_count);
+  s->d_span = s->d_run_uid = s->d_run_off = s->d_count = nullptr;
+  s->dev_cap_runs = 0;
+  MFB_CUDA(cudaMalloc(&s->d_span, 2 * s->cap_runs * sizeof(int32_t)));
+  MFB_CUDA(cudaMalloc(&s->d_run_uid, s->cap_runs * sizeof(int32_t)));
+  MFB_CUDA(cudaMalloc(&s->d_run_off, (s->cap_runs + 1) * sizeof(int32_t)));
+  MFB_CUDA(cudaMalloc(&s->d_count, s->cap_runs * sizeof(int32_t)));
+  s->dev_cap_runs = s->cap_runs;
+  return MFB_OK;
+}
+
+// top-level fields of one serialized mf.Block: the byte range of every User (field 1, length-delimited;
+// blocks.proto:14-16), anything else skipped by wire type.  Offsets are relative to `base`.
+bool walk_block(const uint8_t* p, size_t size, int64_t base, std::vector<int32_t>* spans) {
+  const uint8_t* const begin = p;
+  const uint8_t* const end = p + size;
+  auto varint = [&](uint64_t* v) -> bool {
+    *v = 0;
+    for (int i = 0; i < 10 && p < end; i++) {
+      const uint8_t b = *p++;
+      *v |= (uint64_t)(b & 0x7f) << (7 * i);
+      if (!(b & 0x80)) return true;
+    }
+    return false;
+  };
+  while (p < end) {
+    uint64_t tag, v;
+    if (!varint(&tag)) return false;
+    if (tag == 0x0A) {
+      if (!varint(&v) || v > (uint64_t)(end - p)) return false;
+      spans->push_back((int32_t)(base + (p - begin)));
+      spans->push_back((int32_t)(base + (p - begin) + (int64_t)v));
+      p += v;
+      continue;
+    }
+    switch (tag & 7) {
+      case 0: if (!varint(&v)) return false; break;
+      case 1: if (end - p < 8) return false; p += 8; break;
+      case 2: if (!varint(&v) || v > (uint64_t)(end - p)) return false; p += v; break;
+      case 5: if (end - p < 4) return false; p += 4; break;
+      default: return false;
+    }
+  }
+  return true;
+}
+
+// Stage A of one chunk (frames [f0, f1) of the file): the workers take frames one by one - pread into the pinned raw
+// buffer, walk the users while the bytes are still in the core's cache - then the spans are laid out in file order.
+void stage_host(FilePipe* fp, int device, int fd, size_t f0, size_t f1, FSlot* s) {
+  cudaSetDevice(device);  // (a fresh thread: the event wait and the pinned allocation below need the context's device)
+  s->ok = true;
+  s->nruns = 0;
+  const int64_t byte0 = fp->frame_off[f0] - 4;
+  s->nbytes = (size_t)(fp->frame_off[f1 - 1] + fp->frame_size[f1 - 1] - byte0);
+  if (s->copy_pending) {  // the pinned buffers are free once the copy that last read them is done
+    cudaEventSynchronize(s->copied);
+    s->copy_pending = false;
+  }
+  const size_t nf = f1 - f0;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nthreads = std::min<size_t>(hw, nf);
+  std::vector<std::vector<int32_t>> spans(nf);
+  std::vector<char> ok(nf, 1);
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nf) break;
+      const size_t f = f0 + i;
+      const int64_t off = fp->frame_off[f] - byte0;  // of the payload inside the raw buffer
+      size_t got = 0;
+      const size_t want = fp->frame_size[f];
+      while (got < want) {
+        const ssize_t n = pread(fd, s->h_raw + off + got, want - got, fp->frame_off[f] + (int64_t)got);
+        if (n <= 0) break;
+        got += (size_t)n;
+      }
+      spans[i].reserve(2048);
+      if (got != want || !walk_block(s->h_raw + off, want, off, &spans[i])) ok[i] = 0;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < nthreads; t++) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+  int64_t runs = 0;
+  for (size_t i = 0; i < nf; i++) {
+    if (!ok[i] && s->ok) {
+      s->ok = false;
+      s->bad_frame = f0 + i;
+    }
+    runs += (int64_t)spans[i].size() / 2;
+  }
+  if (!s->ok) return;
+  if (ensure_runs_host(s, runs) != MFB_OK) {
+    s->ok = false;
+    s->bad_frame = (size_t)-1;
+    return;
+  }
+  int64_t at = 0;
+  for (size_t i = 0; i < nf; i++) {
+    if (!spans[i].empty()) memcpy(s->h_span + at, spans[i].data(), spans[i].size() * sizeof(int32_t));
+    at += (int64_t)spans[i].size();
+  }
+  s->nruns = runs;
+}
+
+}  // namespace
+
+void free_file_pipe(Context* c) {
+  FilePipe* fp = (FilePipe*)c->file_pipe;
+  if (!fp) return;
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  if (fp->decode_stream) cudaStreamSynchronize(fp->decode_stream);
+  for (auto& s : fp->slot) free_fslot(&s);
+  if (fp->start) cudaEventDestroy(fp->start);
+  if (fp->decode_stream) {
+    cudaStreamSynchronize(fp->decode_stream);
+    cudaStreamDestroy(fp->decode_stream);
+  }
+  delete fp;
+  c->file_pipe = nullptr;
+}
+
+}  // namespace mfb
+
+static int epoch_from_file_device(Context* c, const char* path, float eta, float lambda, float gb, int mode,
+                                  int64_t tile_ratings, int64_t* ratings_out) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    set_error("cannot open %s", path);
+    return MFB_E_IO;
+  }
+  struct Closer {
+    int fd;
+    ~Closer() { close(fd); }
+  } closer{fd};
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    set_error("cannot stat %s", path);
+    return MFB_E_IO;
+  }
+  const int64_t size = (int64_t)st.st_size;
+  if (size == 0) return MFB_OK;
+  if (!c->file_pipe) c->file_pipe = new FilePipe();
+  FilePipe* fp = (FilePipe*)c->file_pipe;
+  const int64_t mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
+  if (fp->path != path || fp->size != size || fp->mtime_ns != mtime_ns) {
+    // frame boundaries: one 4-byte read per frame (util.h:81)
+    fp->frame_off.clear();
+    fp->frame_size.clear();
+    fp->size = -1;
+    int64_t p = 0;
+    while (size - p >= 4) {
+      uint32_t isize;
+      if (pread(fd, &isize, 4, p) != 4) {
+        set_error("%s: read error at offset %lld", path, (long long)p);
+        return MFB_E_IO;
+      }
+      p += 4;
+      if ((int64_t)isize > size - p) {
+        set_error("%s: truncated frame (%u bytes wanted, %lld left)", path, isize, (long long)(size - p));
+        return MFB_E_IO;
+      }
+      fp->frame_off.push_back(p);
+      fp->frame_size.push_back(isize);
+      p += isize;
+    }
+    fp->path = path;
+    fp->size = size;
+    fp->mtime_ns = mtime_ns;
+  }
+  const size_t nframes = fp->frame_off.size();
+  // chunks = runs of whole frames whose bytes / 9 stay within tile_ratings (see the host path for the bound)
+  std::vector<size_t> chunk_first{0};
+  size_t acc = 0, biggest = 0;
+  for (size_t i = 0; i < nframes; i++) {
+    const size_t fb = (size_t)fp->frame_size[i] + 4;
+    if (acc > 0 && (acc + fb) / 9 + 1 > (size_t)tile_ratings) {
+      chunk_first.push_back(i);
+      biggest = std::max(biggest, acc);
+      acc = 0;
+    }
+    acc += fb;
+  }
+  biggest = std::max(biggest, acc);
+  chunk_first.push_back(nframes);
+  const size_t nchunks = nframes ? chunk_first.size() - 1 : 0;
+  MFB_REQUIRE(biggest < (size_t)INT32_MAX - 64, "tile too large for int32 offsets");
+  const int64_t cap_ratings = (int64_t)(biggest / 9 + 16);
+  for (auto& s : fp->slot)
+    if (int rc = ensure_bytes(&s, biggest, cap_ratings, c->nv)) return rc;
+  if (!c->copy_stream) MFB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!c->stream2) {
+    MFB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    MFB_CUDA(cudaEventCreateWithFlags(&c->ev_s2, cudaEventDisableTiming));
+  }
+  if (!fp->start) MFB_CUDA(cudaEventCreateWithFlags(&fp->start, cudaEventDisableTiming));
+  if (!fp->decode_stream) MFB_CUDA(cudaStreamCreateWithFlags(&fp->decode_stream, cudaStreamNonBlocking));
+  cudaEventRecord(c->ev0, c->stream);
+  // neither the copy stream nor the second compute stream may run ahead of work queued earlier
+  MFB_CUDA(cudaEventRecord(fp->start, c->stream));
+  MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, fp->start, 0));
+  MFB_CUDA(cudaStreamWaitEvent(c->stream2, fp->start, 0));
+  MFB_CUDA(cudaStreamWaitEvent(fp->decode_stream, fp->start, 0));
+  cudaStream_t const main_stream = c->stream;
+  const bool two = c->opt_two_streams != 0 && nchunks > 1 && mode != MFB_MODE_ORDERED;
+  std::future<void> staged[3];
+  auto stage = [&](size_t k) {
+    staged[k % 3] = std::async(std::launch::async, stage_host, fp, c->device, fd, chunk_first[k], chunk_first[k + 1], &fp->slot[k % 3]);
+  };
+  int rc = MFB_OK;
+  // stage B: H2D of the raw bytes and spans, decode kernels, result back - all on the copy stream
+  auto issue = [&](size_t k) -> int {
+    FSlot* s = &fp->slot[k % 3];
+    staged[k % 3].get();
+    if (!s->ok) {
+      if (s->bad_frame == (size_t)-1) return MFB_E_CUDA;
+      set_error("%s: malformed mf.Block in frame %zu", path, s->bad_frame);
+      return MFB_E_IO;
+    }
+    if (int e = ensure_runs_device(s)) return e;  // as large as the host span table
+    // the device raw buffer of this slot is free once the decode that last read it is done
+    if (s->decode_pending) MFB_CUDA(cudaStreamWaitEvent(c->copy_stream, s->decoded, 0));
+    MFB_CUDA(cudaMemcpyAsync(s->d_raw, s->h_raw, s->nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (s->nruns)
+      MFB_CUDA(cudaMemcpyAsync(s->d_span, s->h_span, 2 * s->nruns * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    MFB_CUDA(cudaEventRecord(s->copied, c->copy_stream));
+    s->copy_pending = true;
+    c->h2d_bytes += (int64_t)s->nbytes + 2 * s->nruns * (int64_t)sizeof(int32_t);
+    // ... the tiles once the kernel that last read them is done
+    cudaStream_t ds = fp->decode_stream;
+    MFB_CUDA(cudaStreamWaitEvent(ds, s->copied, 0));
+    if (s->compute_pending) MFB_CUDA(cudaStreamWaitEvent(ds, s->computed, 0));
+    MFB_CUDA(cudaEventRecord(s->decode_begin, ds));
+    if (int e = launch_wire_decode(c, ds, s->d_raw, s->d_span, (int)s->nruns, s->cap_ratings, s->d_run_uid, s->d_run_off,
+                                   s->d_count, s->d_vid, s->d_rating, s->d_hist, s->d_res))
+      return e;
+    MFB_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, 4 * sizeof(int32_t) + sizeof(long long), cudaMemcpyDeviceToHost, ds));
+    MFB_CUDA(cudaEventRecord(s->decoded, ds));
+    s->decode_pending = true;
+    return MFB_OK;
+  };
+
+  int64_t total_ratings = 0, runs_seen = 0, bytes_seen = 0;
+  // MFB_FILE_TIMING=1: where the host thread of this call waits (stderr, one line per epoch)
+  const bool clock_on = getenv("MFB_FILE_TIMING") != nullptr;
+  double t_stage = 0, t_decode = 0, dev_decode_ms = 0;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  if (nchunks > 0) stage(0);
+  if (nchunks > 1) stage(1);
+  for (size_t k = 0; k < nchunks && rc == MFB_OK; k++) {
+    double t0 = now();
+    if (k == 0) rc = issue(0);
+    if (rc == MFB_OK && k + 1 < nchunks) rc = issue(k + 1);  // queued before this thread blocks on chunk k's decode
+    if (rc == MFB_OK && k + 2 < nchunks) stage(k + 2);
+    if (rc != MFB_OK) break;
+    t_stage += now() - t0;
+    t0 = now();
+    FSlot* s = &fp->slot[k % 3];
+    const cudaError_t de = cudaEventSynchronize(s->decoded);
+    t_decode += now() - t0;
+    if (clock_on && de == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s->decode_begin, s->decoded) == cudaSuccess) dev_decode_ms += ms;
+    }
+    if (de != cudaSuccess) {
+      set_error("%s: decode of chunk %zu failed: %s", path, k, cudaGetErrorString(cudaGetLastError()));
+      rc = MFB_E_CUDA;
+      break;
+    }
+    const WireResult res = *s->h_res;
+    if (res.err) {
+      const long long frame_lo = (long long)chunk_first[k], frame_hi = (long long)chunk_first[k + 1];
+      if (res.err == WIRE_E_UID || res.err == WIRE_E_VID) {
+        set_error("%s: uid or vid outside [0,%d) / [0,%d) (frames %lld..%lld, user-run %d of the chunk)", path, c->nu, c->nv,
+                  frame_lo, frame_hi - 1, res.err_run);
+        rc = MFB_E_ARG;
+      } else if (res.err == WIRE_E_CAPACITY) {
+        set_error("%s: chunk %zu decodes to %lld records: records shorter than protobuf writes them", path, k, res.nratings);
+        rc = MFB_E_IO;
+      } else {
+        set_error("%s: malformed mf.User in frames %lld..%lld (user-run %d of the chunk)", path, frame_lo, frame_hi - 1, res.err_run);
+        rc = MFB_E_IO;
+      }
+      break;
+    }
+    if (res.nratings == 0) continue;
+    bytes_seen += (int64_t)s->nbytes;
+    runs_seen += s->nruns;
+    const int64_t est_total_runs = (int64_t)((double)runs_seen * (double)size / (double)std::max<int64_t>(bytes_seen, 1));
+    Dataset view;  // (owns nothing: the device pointers are the slot's)
+    view.used = view.finalized = true;
+    view.nruns = std::max<int64_t>(est_total_runs, s->nruns);  // read for the run bound only; the range is explicit
+    view.nratings = res.nratings;
+    view.d_run_uid = s->d_run_uid;
+    view.d_run_off = s->d_run_off;
+    view.d_vid = s->d_vid;
+    view.d_rating = s->d_rating;
+    view.max_item_share = (double)res.top_count / (double)res.nratings;
+    const bool second = two && (k & 1) == 1;
+    c->stream = second ? c->stream2 : main_stream;
+    c->counter_slot = second ? 2 : 0;
+    c->width_div = two ? 2 : 1;
+    cudaError_t e = cudaStreamWaitEvent(c->stream, s->decoded, 0);
+    if (e == cudaSuccess) rc = launch_sgd(c, &view, eta, lambda, gb, mode, 0, s->nruns);
+    if (e == cudaSuccess && rc == MFB_OK) e = cudaEventRecord(s->computed, c->stream);
+    s->compute_pending = true;
+    c->stream = main_stream;
+    c->counter_slot = 0;
+    c->width_div = 1;
+    if (e != cudaSuccess) {
+      set_error("CUDA error during the streamed epoch: %s", cudaGetErrorString(e));
+      rc = MFB_E_CUDA;
+    }
+    total_ratings += res.nratings;
+  }
+  for (auto& f : staged)
+    if (f.valid()) f.get();
+  cudaEventRecord(c->ev_s2, c->stream2);
+  cudaStreamWaitEvent(c->stream, c->ev_s2, 0);
+  cudaEventRecord(c->ev1, c->stream);
+  c->timed = true;
+  if (rc != MFB_OK) {  // leave nothing queued on buffers whose content is undefined
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(fp->decode_stream);
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  }
+  c->model_age++;
+  if (ratings_out) *ratings_out = total_ratings;
+  if (clock_on)
+    fprintf(stderr, "mfb_sgd_epoch_from_file: %zu chunks, %.1f MB: host thread %.1f ms = %.1f waiting for the pread/walk stage "
+            "+ %.1f waiting for copy+decode + %.1f launching; decode kernels %.1f ms on the device\n", nchunks, size / 1e6,
+            1e3 * (now() - t_begin), 1e3 * t_stage, 1e3 * t_decode, 1e3 * (now() - t_begin - t_stage - t_decode), dev_decode_ms);
+  return MFB_OK;
+}
+
+extern "C" int mfb_sgd_epoch_from_file(mfb_ctx* h, const char* path, float eta, float lambda, float gb, int mode,
+                                       int64_t tile_ratings, int64_t* ratings_out) {
+  MFB_REQUIRE(h && path, "NULL argument");
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC, "bad mode %d", mode);
+  Context* c = &h->c;
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (tile_ratings <= 0) tile_ratings = (int64_t)8 << 20;
+  tile_ratings = std::max<int64_t>(tile_ratings, 1024);
+  if (ratings_out) *ratings_out = 0;
+  return c->opt_file_decode ? epoch_from_file_device(c, path, eta, lambda, gb, mode, tile_ratings, ratings_out)
+                            : epoch_from_file_host(c, path, eta, lambda, gb, mode, tile_ratings, ratings_out);
 }

@@ -128,6 +128,9 @@ struct Context {
   bool planes_allowed = false;  // set around launches that own the item matrix alone (mfb_sgd_epoch, calibration)
   float* d_phi_planes = nullptr;  // scratch copy in plane layout; lives in the placement arena once the search ran
   int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
+  int opt_file_decode = 1;      // out-of-core epoch (mfb_file_epoch.cu): 1 = the raw bytes of the file go to the GPU and
+                                // the records are decoded there (mfb_wire_decode.cu); 0 = decoded by the host cores
+  void* file_pipe = nullptr;    // mfb::FilePipe: pinned / device buffers of that path, kept between epochs
   int opt_epoch_launches = 1;   // diagnostic: mfb_sgd_epoch as this many launches over equal run ranges
   int opt_span_runs = 0;        // burst kernel: runs per claim (0 = by file size: 8, 16 or 32)
   int opt_tail_runs = 2;        // stream/burst kernels: runs per group handed out one by one at the end of a launch
@@ -221,6 +224,8 @@ int launch_admf(Context* c, Dataset* d, float eta, float eta_reg, int loss, floa
 
 // wire decoder (proto_wire.cc): appends every block of a [u32][mf.Block] file to the dataset
 int load_blocks_file(const char* path, Dataset* d);
+// mfb_file_epoch.cu: releases c->file_pipe
+void free_file_pipe(Context* c);
 
 }  // namespace mfb
 

@@ -176,11 +176,16 @@ int64_t mfb_dataset_num_blocks(mfb_ctx* ctx, int ds);
 int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float eta, float lambda,
                             float gb, int mode, int64_t chunk_ratings);
 /* One epoch straight from the [u32 size][mf.Block] training FILE, nothing resident - the reference's own way of
- * running an epoch (read -> parse -> update pipeline, main.cc:45-50, mf.h:24-69): frames are decoded by the host
- * cores into pinned memory chunk by chunk (whole Blocks, about `tile_ratings` records, 0 = 8 Mi), copied into one
- * of TWO device tile buffers and updated there while the next chunk is being decoded.  Device memory for ratings
- * is 2 x tile_ratings x 8 bytes whatever the file size.  File order is kept: in the ORDERED schedule the result
- * equals mfb_sgd_epoch on the loaded file bit for bit.  *ratings (optional) = records processed. */
+ * running an epoch (read -> parse -> update pipeline, main.cc:45-50, mf.h:24-69).  The file is cut into chunks of
+ * whole Blocks (about `tile_ratings` records, 0 = 8 Mi).  Per chunk: the host cores pread the frames into pinned
+ * memory and find the byte range of every serialized mf.User (one jump per user); the RAW bytes go to the GPU, which
+ * decodes the varints / records there (mfb_wire_decode.cu; any valid encoding of blocks.proto, not just the canonical
+ * one) and runs the update kernel on the decoded tiles while the next chunk is copied and the one after that is read.
+ * Three slots of device buffers (raw bytes + 8 bytes per record) whatever the file size; they stay allocated in the
+ * context between epochs.  Option "file_decode" = 0 decodes on the host cores instead (pinned SoA chunks).
+ * File order is kept: in the ORDERED schedule the result equals mfb_sgd_epoch on the loaded file bit for bit.
+ * Errors: MFB_E_IO (unreadable / truncated / malformed), MFB_E_ARG (uid or vid out of range); chunks before the bad
+ * one have been applied.  *ratings (optional) = records processed. */
 int mfb_sgd_epoch_from_file(mfb_ctx* ctx, const char* path, float eta, float lambda, float gb, int mode,
                             int64_t tile_ratings, int64_t* ratings);
 /* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
