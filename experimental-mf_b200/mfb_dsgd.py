@@ -99,6 +99,50 @@ class DsgdWorker:
         self.ctx.close()
 
 
+def yahoo_subrecord(args, rank, world, local, stream, timed):
+    """Yahoo-Music-shaped SGD k=128 (1,000,990 users x 624,961 items, 252 M ratings) over the ring: every rank holds its
+    users' ratings and one item block at a time (40 MB at 8 ranks: L2-resident, where the whole matrix, 320 MB, is not)."""
+    import torch
+    import torch.distributed as dist
+    from bench import ETA0, GAM, GB, LAMBDA, UNIT, WORKLOADS, workload_config
+    nu, nv, nnz, k, test_frac = WORKLOADS["yahoo"]
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(mb.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    u0, u1 = user_range(nu, rank, world)
+    t0 = time.time()
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=test_frac, user_begin=u0, user_end=u1))
+    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, bytes(uid.cpu().numpy().tobytes()))
+    w.ctx.set_stream(stream.cuda_stream)
+    setup_s = time.time() - t0
+    tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    ntrain = int(tot[0])
+    w.ctx.dsgd_epoch(w.cell_ds, w.bounds, 0.0, 0.0, GB, mb.MODE_ATOMIC, w.halves, 1)  # connections, placement
+    torch.cuda.synchronize()
+    epoch = [0]
+
+    def step():
+        epoch[0] += 1
+        w.epoch(mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mb.MODE_ATOMIC)
+
+    for _ in range(args.warmup):
+        step()
+    total_ms, _ = timed(step, args.steps)
+    timeline = [float(x) for x in w.ctx.dsgd_timeline(world * w.halves)]
+    sse, n = w.global_sse(GB)
+    shape = w.ctx.last_launch()
+    w.close()
+    return {"workload": workload_config("yahoo", world)["workload"], "ms_per_epoch": total_ms / args.steps,
+            "updates_per_s": ntrain * args.steps / (total_ms * 1e-3), "unit": UNIT, "train_ratings": ntrain,
+            "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
+            "test_rmse_after_%d_epochs" % epoch[0]: float(np.sqrt(sse / max(n, 1))),
+            "first_epoch_ring_turns": w.first_epoch_rotations, "launch": shape, "setup_s": round(setup_s, 1),
+            "rank0_timeline_ms_wait_kernel": timeline,
+            "note": "compare with configs.C5_yahoo_mf_k128_1gpu of the N = 1 line (same data, same epochs, one GPU)"}
+
+
 def bench(args, wl, shape, rank, world, local, config):
     """bench.py --gpus N (N > 1), launched by torch.distributed.run."""
     import torch
@@ -219,6 +263,15 @@ def bench(args, wl, shape, rank, world, local, config):
     sse, n = sse_host[-1]
     launches = launches_resident + launches_e2e  # this rank's kernels inside the two timed regions
     shape = w.ctx.last_launch()
+    w.close()
+
+    # ---- C5: the Yahoo-Music shape on the same ring (BASELINE.json configs[4]); resident epochs only -----------------
+    c5 = None
+    if wl == "netflix" and not args.no_configs and args.yahoo:
+        try:
+            c5 = yahoo_subrecord(args, rank, world, local, stream, timed)
+        except Exception as e:  # a sub-record must not take the headline down with it
+            c5 = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = value * bytes_per_update(k) / 1e9 / world  # per GPU
@@ -252,7 +305,7 @@ def bench(args, wl, shape, rank, world, local, config):
                      "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
                      "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch on a communication stream",
                      "rank0_timeline_ms_wait_kernel": timeline},
+            "configs": {"C5_yahoo_mf_k128": c5} if c5 else None,
         }
         print(json.dumps(line))
-    w.close()
     dist.destroy_process_group()
