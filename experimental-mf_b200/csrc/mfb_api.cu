@@ -489,6 +489,8 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     c->opt_phi_planes = value;
   } else if (!strcmp(name, "two_streams")) {
     c->opt_two_streams = value != 0;
+  } else if (!strcmp(name, "sgld_flat")) {
+    c->opt_sgld_flat = value;
   } else if (!strcmp(name, "file_decode")) {
     MFB_REQUIRE(value == 0 || value == 1, "file_decode must be 0 (host cores) or 1 (device)");
     c->opt_file_decode = value;

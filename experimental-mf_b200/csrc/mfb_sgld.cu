@@ -329,6 +329,225 @@ __global__ void __launch_bounds__(256) sgld_epoch_kernel(const SgldArgs a) {
   }
 }
 
+// ---- the parallel schedule, sub-warp organisation (round 2) -------------------------------------------------------
+// sgld_epoch_kernel above gives a whole warp to one user-run at k = 128: ~205 of its 345 warp instructions per record
+// are the generator (2 Philox blocks + 2 Box-Muller quadruples + the bias pair per lane), the other ~140 are the
+// update and the bookkeeping of the record - scalar work that one warp instruction does for ONE record.  Here a row
+// is owned by LPR = 16 lanes holding VPL = 2 float4 each (k = 64, 32: 8 and 4 lanes), a warp advances 32/LPR user-runs at once and every
+// non-generator instruction serves 32/LPR records; the generator work per record is unchanged (the same
+// (t, row, chunk, kind) -> normal function, evaluated chunk by chunk and consumed at once, so no noise row is ever
+// held in registers).  The loop is FLAT: all groups of a warp execute the same step, the claim / retire of a
+// user-run is the only divergent path (one run per group in flight, claimed from the same queue as before).
+// lambda_u / lambda_v live in shared memory (the same for every group), the factor row as the run found it in a
+// per-lane shared-memory slot (the user row leaves as a reduction of its increment, like the item row).
+// The ordered schedule and dim > 128 keep the kernel above.
+template <int VPL>
+struct FlatItem {  // the item side of one record: row, bias, weight, id
+  Row<VPL> f;
+  float bv, vr;
+  int v;
+};
+
+// EXACT: the row is exactly LPR*VPL float4 (k = 32, 64, 128): no per-vector predicates, no padding selects
+template <int LPR, int VPL, bool EXACT>
+__global__ void __launch_bounds__(128) sgld_flat_kernel(const SgldArgs a) {
+  extern __shared__ float4 flat_smem[];
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int ROW4 = LPR * VPL;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const unsigned m = group_mask<LPR>();
+  float4* lam = flat_smem;                              // [2][ROW4]: lambda_u, lambda_v (zero padded)
+  float4* t0s = flat_smem + 2 * ROW4 + threadIdx.x;     // [VPL][blockDim.x]: this lane's part of the row at run start
+  for (int q = threadIdx.x; q < ROW4; q += blockDim.x) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    lam[q] = q < a.nvec ? __ldg(reinterpret_cast<const float4*>(a.lambda_u) + q) : z;
+    lam[ROW4 + q] = q < a.nvec ? __ldg(reinterpret_cast<const float4*>(a.lambda_v) + q) : z;
+  }
+  __syncthreads();
+  const float noise_scale = a.temp * a.eta;
+  const float4* __restrict__ phi4 = reinterpret_cast<const float4*>(a.phi);
+
+  bool act = false, done = false;
+  int uid = 0, j = 0, lo = 0, hi = 0, uc = 1;
+  Row<VPL> t;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) t.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bu = 0.f, bu_in = 0.f, au = 0.f, cbu = 1.f;
+  // records [chunk, chunk+LPR) of the run, one per lane, and the LPR after them
+  int c_vid = 0, c_vc = 1, n_vid = 0, n_vc = 1;
+  float c_r = 0.f, n_r = 0.f;
+  // two register sets for the item side: a step works on one and requests the next record's row into the other
+  // (the main loop is unrolled twice, so no set is ever copied)
+  FlatItem<VPL> A, B;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) A.f.v[i] = B.f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  A.bv = B.bv = A.vr = B.vr = 0.f;
+  A.v = B.v = 0;
+
+  auto load_chunk = [&](int q0, int* vid, float* r, int* vc) {
+    const int q = q0 + gl;
+    *vid = q < hi ? __ldcs(a.vid + q) : 0;
+    *r = q < hi ? __ldcs(a.rating + q) : 0.f;
+    *vc = q < hi ? __ldcs(a.vc + q) : 1;
+  };
+  auto fetch = [&](FlatItem<VPL>& it, int item) {
+    it.v = item;
+    const float4* p = phi4 + (int64_t)item * a.nvec + gl;
+#pragma unroll
+    for (int i = 0; i < VPL; i++)
+      if (EXACT || gl + i * LPR < a.nvec) it.f.v[i] = __ldcg(p + i * LPR);
+    it.bv = __ldcg(a.bv + item);
+    it.vr = __ldg(a.vr + item);
+  };
+  // claim a user-run (divergent; once per run and group); its first item row goes into `it`
+  auto claim = [&](FlatItem<VPL>& it) {
+    if (!act && !done) {
+      int run = 0;
+      if (gl == 0) run = atomicAdd(a.counter, 1);
+      run = __shfl_sync(m, run, 0, LPR);
+      if (run >= a.nruns) {
+        done = true;
+      } else {
+        lo = __ldg(a.run_off + run);
+        hi = __ldg(a.run_off + run + 1);
+        if (lo < hi) {
+          uid = __ldg(a.run_uid + run);
+          t = load_row<LPR, VPL>(a.theta, uid, a.nvec, gl);
+          bu = __ldcg(a.bu + uid);
+          const float ur = __ldg(a.ur + uid);
+          uc = __ldg(a.run_uc + run);
+          load_chunk(lo, &c_vid, &c_r, &c_vc);
+          load_chunk(lo + LPR, &n_vid, &n_r, &n_vc);
+          fetch(it, __shfl_sync(m, c_vid, 0, LPR));
+#pragma unroll
+          for (int i = 0; i < VPL; i++) t0s[i * blockDim.x] = t.v[i];
+          bu_in = bu;
+          au = -a.eta * ur * a.bound;                                          // dpmf.h:78
+          cbu = (float)(1.0 - (double)(a.eta * a.lambda_ub * ur * a.bound));    // dpmf.h:84
+          j = lo;
+          act = true;
+        }
+      }
+    }
+  };
+  // one record per group (converged: every shuffle is a full-warp instruction of width LPR; groups without a run
+  // compute on stale registers and write nothing)
+  auto step = [&](FlatItem<VPL>& cur, FlatItem<VPL>& nxt) {
+    const int b = (j - lo) & (LPR - 1);
+    const float r = __shfl_sync(FULL, c_r, b, LPR);
+    const int vc = __shfl_sync(FULL, c_vc, b, LPR);
+    const int item = cur.v;
+    // the next record of the run: its row is requested now and used one step from here
+    const bool more = act && j + 1 < hi;
+    if (b + 1 == LPR) {  // ... it opens the next chunk of LPR records
+      c_vid = n_vid;
+      c_r = n_r;
+      c_vc = n_vc;
+      if (more) load_chunk(j + 1 + LPR, &n_vid, &n_r, &n_vc);
+    }
+    const int nitem = __shfl_sync(FULL, c_vid, (b + 1) & (LPR - 1), LPR);
+    if (more) fetch(nxt, nitem);
+
+    const float su = mufu_sqrt(noise_scale * (float)uc), sv = mufu_sqrt(noise_scale * (float)vc);  // dpmf.h:67-70
+    const float av = -a.eta * cur.vr * a.bound;                                                   // dpmf.h:81
+    // lazy noise of both rows, chunk by chunk: theta += su * xi_u, phi += sv * xi_v
+    uint32_t spare_u = 0, spare_v = 0;
+    Row<VPL> nz;  // sv * xi_v: part of the item row's increment
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const uint32_t chunk = (uint32_t)(gl + i * LPR);
+      const uint4 xu = philox4x32_10_rk(make_uint4((uint32_t)j, (uint32_t)uid, chunk, 2u * a.round), a.rk);
+      const uint4 xv = philox4x32_10_rk(make_uint4((uint32_t)j, (uint32_t)item, chunk, 1u + 2u * a.round), a.rk);
+      if (i == 0) {
+        spare_u = spare_bits24(xu);
+        spare_v = spare_bits24(xv);
+      }
+      float4 zu = box_muller4_fast(xu), zv = box_muller4_fast(xv);
+      if (!EXACT && a.dim < 4 * ROW4) {  // coordinates >= dim are padding: they stay exactly zero
+        const int c = 4 * (int)chunk;
+        if (c + 0 >= a.dim) zu.x = zv.x = 0.f;
+        if (c + 1 >= a.dim) zu.y = zv.y = 0.f;
+        if (c + 2 >= a.dim) zu.z = zv.z = 0.f;
+        if (c + 3 >= a.dim) zu.w = zv.w = 0.f;
+      }
+      float4 tt = t.v[i], f1 = cur.f.v[i];
+      tt.x = fmaf(su, zu.x, tt.x); tt.y = fmaf(su, zu.y, tt.y); tt.z = fmaf(su, zu.z, tt.z); tt.w = fmaf(su, zu.w, tt.w);
+      nz.v[i] = make_float4(sv * zv.x, sv * zv.y, sv * zv.z, sv * zv.w);
+      f1.x += nz.v[i].x; f1.y += nz.v[i].y; f1.z += nz.v[i].z; f1.w += nz.v[i].w;
+      d = fmaf(tt.x, f1.x, d); d = fmaf(tt.y, f1.y, d); d = fmaf(tt.z, f1.z, d); d = fmaf(tt.w, f1.w, d);
+      t.v[i] = tt;
+      cur.f.v[i] = f1;
+    }
+    // the two bias values from the spare bits of chunks 0 and 1 of either stream: lane 0 evaluates the user's,
+    // lane 1 the item's, after one exchange (see noise_pair)
+    const uint32_t other = __shfl_xor_sync(FULL, gl == 0 ? spare_v : spare_u, 1, LPR);
+    const uint32_t s0 = gl == 0 ? spare_u : other, s1 = gl == 0 ? other : spare_v;
+    const float bn = box_muller_bias_fast(s0, s1);
+    const float xbu = __shfl_sync(FULL, bn, 0, LPR), xbv = __shfl_sync(FULL, bn, 1, LPR);
+    const float bu1 = fmaf(su, xbu, bu);
+    const float bv_in = cur.bv;
+    const float bv1 = fmaf(sv, xbv, bv_in);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o, LPR);
+    const float e = a.scal * (r - d - bu1 - bv1 - a.gb);                        // dpmf.h:72-75
+    if (act) {
+      // the item row receives its INCREMENT (noise + drift + gradient step) as 128-bit reductions
+      float4* dst = reinterpret_cast<float4*>(a.phi) + (int64_t)item * a.nvec + gl;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const float4 lu = lam[gl + i * LPR], lv = lam[ROW4 + gl + i * LPR];
+        float4 tt = t.v[i];
+        const float4 f1 = cur.f.v[i];
+        float4 df;
+        df.x = fmaf(av * lv.x, f1.x, fmaf(e, tt.x, nz.v[i].x));                 // dpmf.h:76,80-82
+        df.y = fmaf(av * lv.y, f1.y, fmaf(e, tt.y, nz.v[i].y));
+        df.z = fmaf(av * lv.z, f1.z, fmaf(e, tt.z, nz.v[i].z));
+        df.w = fmaf(av * lv.w, f1.w, fmaf(e, tt.w, nz.v[i].w));
+        tt.x = fmaf(e, f1.x, fmaf(au * lu.x, tt.x, tt.x));                      // dpmf.h:77-79
+        tt.y = fmaf(e, f1.y, fmaf(au * lu.y, tt.y, tt.y));
+        tt.z = fmaf(e, f1.z, fmaf(au * lu.z, tt.z, tt.z));
+        tt.w = fmaf(e, f1.w, fmaf(au * lu.w, tt.w, tt.w));
+        t.v[i] = tt;
+        if (EXACT || gl + i * LPR < a.nvec)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i * LPR), "f"(df.x), "f"(df.y),
+                       "f"(df.z), "f"(df.w) : "memory");
+      }
+      if (gl == 0) {
+        const float bv_new = fmaf(1.0f - a.eta * a.lambda_vb * cur.vr * a.bound, bv1, e);  // dpmf.h:85
+        atomicAdd(a.bv + item, bv_new - bv_in);
+      }
+      bu = fmaf(cbu, bu1, e);                                                   // dpmf.h:84
+      uc = 1;  // consecutive records of a run are consecutive clock ticks
+      j++;
+      if (j == hi) {  // retire the run: the user row leaves as the reduction of what the run added to it
+        float4* dt = reinterpret_cast<float4*>(a.theta) + (int64_t)uid * a.nvec + gl;
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+          const float4 t0 = t0s[i * blockDim.x];
+          if (EXACT || gl + i * LPR < a.nvec)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dt + i * LPR), "f"(t.v[i].x - t0.x),
+                         "f"(t.v[i].y - t0.y), "f"(t.v[i].z - t0.z), "f"(t.v[i].w - t0.w) : "memory");
+        }
+        if (gl == 0) atomicAdd(a.bu + uid, bu - bu_in);
+        act = false;
+      }
+    }
+  };
+
+  for (;;) {
+    claim(A);
+    if (__all_sync(FULL, done)) break;
+    __syncwarp();
+    step(A, B);
+    claim(B);
+    if (__all_sync(FULL, done)) break;
+    __syncwarp();
+    step(B, A);
+  }
+}
+
 // K6: DPMF::finish_noise (model.cc:312-332): every row receives the noise it has not yet been
 // given: sqrt(temp*eta*(ntrain - last_touch)) * xi.  One group per row, pure streaming.
 struct FlushArgs {
@@ -402,8 +621,55 @@ __global__ void __launch_bounds__(256) col_sqnorm_kernel(const float* mat, const
 // ------------------------------------------------------------------------------------------
 namespace {
 
+// parallel schedule, sub-warp organisation: FL lanes x FV float4 per row
+template <int FL, int FV>
+int launch_sgld_flat(Context* c, const Dataset* d, const SgldArgs& a) {
+  auto k = a.nvec == FL * FV ? sgld_flat_kernel<FL, FV, true> : sgld_flat_kernel<FL, FV, false>;
+  // CTAs of at most 4 warps (155 registers per thread at FV = 4: three such CTAs per SM)
+  int per_sm = 0;
+  const size_t smem4 = (size_t)(2 * FL * FV + FV * 128) * sizeof(float4);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, smem4);
+  per_sm = std::max(per_sm, 1);
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  const int gpw = 32 / FL;  // groups per warp
+  int64_t groups = std::min<int64_t>((int64_t)c->sm_count * per_sm * 4 * gpw, std::max(a.nruns, 1));
+  // one record between gather and write-back per group; the step of a stale update is
+  // scal = eta*ntrain*bound*lambda_r (dpmf.h:46), the counterpart of plain SGD's eta
+  groups = bounded_groups(c, groups, d->max_item_share, d->nruns, 1.0, a.scal);
+  const int64_t warps = (groups + gpw - 1) / gpw;
+  int grid, threads;
+  if (warps <= c->sm_count) {
+    grid = (int)warps;
+    threads = 32;
+  } else {
+    const int64_t per = (warps + c->sm_count - 1) / c->sm_count;  // warps per SM
+    const int ctas = (int)((per + 3) / 4);
+    threads = 32 * (int)((per + ctas - 1) / ctas);
+    grid = c->sm_count * ctas;
+  }
+  c->last_grid = grid;
+  c->last_threads = threads;
+  const size_t smem = (size_t)(2 * FL * FV + FV * threads) * sizeof(float4);
+  k<<<grid, threads, smem, c->stream>>>(a);
+  MFB_CUDA(cudaGetLastError());
+  c->launches++;
+  return MFB_OK;
+}
+
 template <int LPR, int VPL>
 int launch_sgld_t(Context* c, const Dataset* d, const SgldArgs& a, int mode) {
+  if (mode != MFB_MODE_ORDERED && c->opt_sgld_flat) {
+    // rows of 4*nvec floats over the fewest lanes that hold them with 4 float4 each
+    // (k = 64 as 8 lanes x 2 float4: four runs per warp; 4 x 4 - eight runs - was slower than the warp-per-run
+    // kernel's two, 30.3 against 23.6 ms)
+    // (k = 128 as 8 x 4 - four runs per warp, 234 warp instructions per record - leaves 3 warps per scheduler under
+    // the run bound and stalls on fixed-latency dependencies: 34.8 ms, and 53 / 41 ms in the narrow epochs 1 - 2;
+    // 16 x 2: 33.1 ms and 37 / 33 ms.  Option sgld_flat = 2 selects 8 x 4.)
+    if (a.nvec > 16 && a.nvec <= 32 && c->opt_sgld_flat == 2) return launch_sgld_flat<8, 4>(c, d, a);
+    if (a.nvec > 16 && a.nvec <= 32) return launch_sgld_flat<16, 2>(c, d, a);    // k <= 128
+    if (a.nvec > 8 && a.nvec <= 16) return launch_sgld_flat<8, 2>(c, d, a);      // k <= 64
+    if (a.nvec > 4 && a.nvec <= 8) return launch_sgld_flat<4, 2>(c, d, a);       // k <= 32
+  }
   if (mode == MFB_MODE_ORDERED) {
     sgld_epoch_kernel<LPR, VPL, MFB_MODE_ORDERED><<<1, 32, 0, c->stream>>>(a);
   } else {

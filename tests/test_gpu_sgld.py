@@ -123,6 +123,53 @@ def test_ordered_sgld_with_philox_noise_matches_oracle(dim):
     assert _sgld_pair(dim, 0.5, 0.5, 1.3, False) <= 1e-5
 
 
+@pytest.mark.parametrize("flat", [1, 0], ids=["sub-warp kernel", "warp-per-run kernel"])
+@pytest.mark.parametrize("dim", [20, 32, 64, 100, 128])
+def test_parallel_sgld_on_conflict_free_data_equals_the_serial_oracle(dim, flat):
+    """Production schedule of the dpmf epoch (both kernels: sgld_flat_kernel and the warp-per-run one) on data where
+    the order cannot matter - every item rated once, one run per user - against the serial oracle with the same
+    Philox noise stream.  With little noise (temp = 1e-4) the rows agree to 1e-5; with the noise dominating the rows
+    (temp = 0.5: every item is touched once, so its lazy noise covers the whole epoch) to 2e-4, the accuracy of the
+    MUFU lg2 / sin / cos the production schedule builds its normals with (the ordered schedule uses libm).  The two
+    kernels agree with each other far more closely than either does with libm (measured 2e-8)."""
+    L = ol.oracle()
+    rng = np.random.default_rng(dim)
+    nruns, per = 700, 23
+    n = nruns * per
+    lens = rng.integers(1, 2 * per, nruns)
+    lens[-1] += n - lens.sum() if lens.sum() < n else 0
+    off = np.r_[0, np.cumsum(lens)]
+    n = int(off[-1])
+    train = ol.Dataset(np.r_[np.arange(0, nruns, 50), nruns], rng.permutation(nruns), off, rng.permutation(n),
+                       rng.integers(1, 6, n))
+    nu, nv = nruns, n
+    for eps, lam_r, tmp, tol in ((0.0, 0.0, 1e-4, 1e-5), (0.5, 1.3, 1e-4, 1e-5), (0.5, 1.3, 0.5, 2e-4)):
+        m = ol.Model(nu, nv, dim, seed=4, scale=0.1)
+        c, d, ntrain = dp_ctx(m, train)
+        c.set_option("sgld_flat", flat)
+        eta, temp = np.float32(2e-2 / ntrain), np.float32(tmp)
+        bound = mb.lib().mfb_dp_bound(eps, 0, nv)
+        lam = (np.random.default_rng(1).uniform(0.5, 2.0, 2 * dim)).astype(np.float32)
+        c.upload(mb.LAMBDA_U, lam[:dim])
+        c.upload(mb.LAMBDA_V, lam[dim:])
+        ur, vr = c.download(mb.UR), c.download(mb.VR)
+        lu, lv = lam[:dim].copy(), lam[dim:].copy()
+        gcu, gcv = np.zeros(nu, np.uint64), np.zeros(nv, np.uint64)
+        st = MfoDpState(eta, temp, bound, ntrain, lam_r, 0.7, 0.9, _p(lu, f32p), _p(lv, f32p), _p(ur, f32p),
+                        _p(vr, f32p), 0, _p(gcu, u64p), _p(gcv, u64p))
+        mm, dd = m.as_mfo(), train.as_mfo()
+        fn = C.cast(L.mfo_noise_from_philox, C.c_void_p)
+        for ep in (1, 2):
+            ctx = MfoNoisePhilox(99, ep)
+            p = mb.SgldParams(eta, temp, bound, ntrain, lam_r, 0.7, 0.9, 99, ep, 0, 0)
+            c.sgld_epoch(d, p, GB, mb.MODE_HOGWILD)
+            L.mfo_sgld_epoch(C.byref(mm), C.byref(dd), C.byref(st), GB, fn, C.byref(ctx))
+            assert model_rel_err(c, m) <= tol, (eps, lam_r, ep, model_rel_err(c, m))
+            c.sgld_flush_noise(d, p)
+            L.mfo_finish_noise(C.byref(mm), C.byref(st), fn, C.byref(ctx))
+        c.close()
+
+
 @pytest.mark.parametrize("mode", [mb.MODE_ORDERED, mb.MODE_HOGWILD])
 def test_noise_statistics_per_epoch_invariant(mode):
     """with the drift switched off (lambda_r = lambda_* = 0) one epoch + flush adds to

@@ -14,7 +14,8 @@ print("file %.1f MB, %d ratings, %d runs, %d blocks" % (os.path.getsize(path) / 
 c = mb.Context(nu, nv, k); c.init_normal(1, 1e-2)
 dte = c.dataset_from_blocks(te)
 ep = 0
-for decode, tile, two in ((1, 0, 1), (1, 16 << 20, 1), (1, 4 << 20, 1), (1, 0, 0), (0, 0, 1)):
+VARIANTS = ((1, 0, 1), (1, 16 << 20, 1), (1, 4 << 20, 1), (1, 0, 0), (0, 0, 1))
+for decode, tile, two in VARIANTS[: int(os.environ.get("ONLY", len(VARIANTS)))]:
     c.set_option("file_decode", decode); c.set_option("two_streams", two)
     secs, kms = [], []
     for rep in range(4 if decode else 2):
