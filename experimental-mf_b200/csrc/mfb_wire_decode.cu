@@ -126,32 +126,45 @@ __global__ void __launch_bounds__(256) wire_count_kernel(const uint64_t* __restr
   count[r] = n;
 }
 
-// run_off[0] = 0, run_off[r+1] = count[0] + ... + count[r]; one block (a chunk holds ~1e5 runs)
+// run_off[0] = 0, run_off[r+1] = count[0] + ... + count[r]; one block (a chunk holds ~1e5 runs): every warp owns a
+// contiguous slice and walks it 32 counts at a time (coalesced), first to sum it, then - once the sums of the slices
+// before it are known - to write the running totals
 __global__ void __launch_bounds__(1024) wire_scan_kernel(const int32_t* __restrict__ count, int nruns,
                                                          int32_t* __restrict__ run_off, WireResult* res) {
-  __shared__ long long part[1024];
-  const int t = threadIdx.x;
-  const int per = (nruns + 1023) / 1024;
-  const int lo = min(t * per, nruns), hi = min(lo + per, nruns);
+  __shared__ long long part[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int per = ((nruns + 31) / 32 + 31) & ~31;  // counts per warp, a multiple of 32
+  const int lo = min(w * per, nruns), hi = min(lo + per, nruns);
   long long s = 0;
-  for (int i = lo; i < hi; i++) s += count[i];
-  part[t] = s;
+  for (int i = lo + lane; i < hi; i += 32) s += count[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) part[w] = s;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan of the partial sums
-    const long long v = t >= d ? part[t - d] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  if (w == 0) {  // exclusive scan of the 32 slice sums
+    long long v = part[lane], x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    part[lane] = x - v;
+    if (lane == 31) {
+      res->nratings = x;
+      if (x > 0x7fffffffLL) report(res, WIRE_E_FORMAT, -1);
+    }
   }
-  long long run = t ? part[t - 1] : 0;
-  if (t == 0) run_off[0] = 0;
-  for (int i = lo; i < hi; i++) {
-    run += count[i];
-    run_off[i + 1] = (int32_t)run;
-  }
-  if (t == 1023) {
-    res->nratings = part[1023];
-    if (part[1023] > 0x7fffffffLL) report(res, WIRE_E_FORMAT, -1);
+  __syncthreads();
+  long long run = part[w];
+  if (threadIdx.x == 0) run_off[0] = 0;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const long long c = i < hi ? count[i] : 0;
+    long long x = c;
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (i < hi) run_off[i + 1] = (int32_t)(run + x);
+    run += __shfl_sync(0xffffffffu, x, 31);
   }
 }
 
