@@ -453,10 +453,17 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
             return {"skipped": "no golden file %s" % gname}
         traj, kms, ntrain, lam_r = config_dpmf(mb, np, tr, te, nu, nv, k, g, device)
         ref = g["test_rmse"]
-        prof, prof_src = profiled("sgld")
+        prof, prof_src = profiled("sgld_flat")
+        bound = "instruction issue (Philox4x32-10 + Box-Muller per coordinate)"
+        if prof and k == 128:  # the committed capture is the k = 128 launch
+            try:
+                inst = float(prof["smsp__inst_executed.sum"]["value"])
+                issue = float(prof["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"])
+                bound += ": %.0f warp instructions per record, issue slots %.0f %% busy" % (inst / ntrain, issue)
+            except (KeyError, ValueError):
+                pass
         return {"workload": g["config"], "ms_per_epoch": kms, "updates_per_s": ntrain / kms * 1e3,
-                "bound": "instruction issue (Philox4x32-10 + Box-Muller per coordinate): %s warp instructions per record"
-                         % (prof.get("warp_inst_per_record") if prof else "see profiles/"), "profile": prof_src,
+                "kernel": "sgld_flat_kernel (sub-warp per run, flat loop)", "bound": bound, "profile": prof_src,
                 "test_rmse": traj[-1], "test_rmse_reference": ref[-1], "rmse_abs_diff": abs(traj[-1] - ref[-1]),
                 "rmse_trajectory": traj, "rmse_reference_trajectory": ref, "lambda_r": lam_r, "lambda_r_reference": g["lambda_r"][-1],
                 "reference": "reference SgldFilter/finish_noise/sample_hyper in file order (tests/golden/fullsize/%s.json); "
