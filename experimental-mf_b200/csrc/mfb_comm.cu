@@ -75,17 +75,136 @@ struct Comm {
   cudaEvent_t computed[MFB_MAX_HALVES] = {nullptr}, shifted[MFB_MAX_HALVES] = {nullptr};
   bool shift_pending[MFB_MAX_HALVES] = {false};
   double* d_red = nullptr;  // [2] sse, count
+  // Peer-memory ring (mfb_comm_ipc_export / import): the shift PUSHES the block into the neighbour's copy of phi / bv
+  // over NVLink (its allocations are mapped here through CUDA IPC) and then raises a sequence number in the
+  // neighbour's flag word; the neighbour's compute stream waits for that number on the device.  No NCCL call, no
+  // host involvement, one copy per array.
+  float* peer_phi = nullptr;   // rank-1's phi / bv / flags, mapped
+  float* peer_bv = nullptr;
+  void *map_phi = nullptr, *map_bv = nullptr;  // what cudaIpcOpenMemHandle returned (allocation bases)
+  unsigned* peer_flags = nullptr;
+  unsigned* d_flags = nullptr;  // [MFB_MAX_HALVES + 1]: [slot] = shifts of that piece slot that have arrived here; [last] = timeout seen
+  unsigned seq[MFB_MAX_HALVES] = {0};  // shifts issued per piece slot (the same count on both ends of a link)
+  unsigned* h_err = nullptr;    // pinned copy of the timeout word
+  bool p2p = false;
   // diagnostic timeline of the most recent epoch (mfb_dsgd_timeline): events on the compute stream
   // at the start of the epoch, after every cell kernel and after every wait for the ring shift
   std::vector<cudaEvent_t> marks;
   int nmarks = 0;
 };
 
+// base and size of the cudaMalloc allocation that holds p
+static bool cuda_range(const void* p, void** base, size_t* size) {
+  typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+  static GetRange fn = (GetRange)dlsym(RTLD_DEFAULT, "cuMemGetAddressRange_v2");
+  if (!fn) {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = (GetRange)dlsym(h, "cuMemGetAddressRange_v2");
+  }
+  unsigned long long b = 0;
+  if (!fn || fn(&b, size, (unsigned long long)(uintptr_t)p) != 0) return false;
+  *base = (void*)(uintptr_t)b;
+  return true;
+}
+
+// the sequence number of a delivered shift, visible to the neighbour after everything this stream copied before it
+__global__ void ring_flag_set_kernel(unsigned* peer_flag, unsigned seq) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned*>(peer_flag) = seq;
+  __threadfence_system();
+}
+// wait (on the device, one thread) until the neighbour has delivered shift `seq`; gives up after `timeout_ns` and
+// says so in *err - a lost neighbour must not hang the GPU
+__global__ void ring_flag_wait_kernel(const unsigned* flag, unsigned seq, unsigned long long timeout_ns, unsigned* err) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*reinterpret_cast<const volatile unsigned*>(flag) - seq) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) {
+      *err = seq ? seq : 1u;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
 }  // namespace mfb
 
 using namespace mfb;
 
 extern "C" {
+
+// ---- peer-memory ring --------------------------------------------------------------------------------------------
+// out208 = three cudaIpcMemHandle_t (64 bytes each) - the allocations that hold this rank's phi, bv and flag words -
+// followed by two uint64: the byte offsets of phi and bv inside their allocations (after the placement search the two
+// live inside its arena).  Fails (MFB_E_ARG) while the placement search may still relocate the item matrix (matrices
+// that fit the L2, before their first parallel epoch): the mapping would go stale.
+int mfb_comm_ipc_export(mfb_ctx* h, void* out208) {
+  MFB_REQUIRE(h && out208, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m, "communicator not initialised");
+  const size_t phi_bytes = (size_t)c->nv * c->stride * sizeof(float);
+  MFB_REQUIRE(c->opt_placement_trials <= 1 || phi_bytes > ((size_t)64 << 20) || c->placement_done[0],
+              "the placement search may still move the item matrix: run one epoch first");
+  MFB_CUDA(cudaSetDevice(c->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!m->d_flags) {
+    MFB_CUDA(cudaMalloc(&m->d_flags, (MFB_MAX_HALVES + 1) * sizeof(unsigned)));
+    MFB_CUDA(cudaMemset(m->d_flags, 0, (MFB_MAX_HALVES + 1) * sizeof(unsigned)));
+    MFB_CUDA(cudaMallocHost(&m->h_err, sizeof(unsigned)));
+    *m->h_err = 0;
+  }
+  auto base_of = [&](const float* p, uint64_t* off) -> const void* {  // the allocation a pointer lives in
+    const char* q = (const char*)p;
+    if (c->placement_arena && q >= c->placement_arena) {
+      // (slots of the arena are laid out behind each other; the arena is one cudaMalloc)
+      size_t asize = 0;
+      void* abase = nullptr;
+      if (cuda_range(c->placement_arena, &abase, &asize) && q < (const char*)abase + asize) {
+        *off = (uint64_t)(q - (const char*)abase);
+        return abase;
+      }
+    }
+    *off = 0;
+    return p;
+  };
+  cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)out208;
+  uint64_t off[2];
+  const void* bphi = base_of(c->arr[MFB_PHI], &off[0]);
+  const void* bbv = base_of(c->arr[MFB_BV], &off[1]);
+  MFB_CUDA(cudaIpcGetMemHandle(&out[0], (void*)bphi));
+  MFB_CUDA(cudaIpcGetMemHandle(&out[1], (void*)bbv));
+  MFB_CUDA(cudaIpcGetMemHandle(&out[2], m->d_flags));
+  memcpy((char*)out208 + 192, off, sizeof off);
+  return MFB_OK;
+}
+
+// in208 = what rank-1 (the rank this one sends to) exported.  From here on the ring shifts go through peer memory.
+int mfb_comm_ipc_import(mfb_ctx* h, const void* in208) {
+  MFB_REQUIRE(h && in208, "NULL argument");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  MFB_REQUIRE(m && m->d_flags, "export this rank's handles first");
+  MFB_REQUIRE(!m->p2p, "peer memory already mapped");
+  MFB_CUDA(cudaSetDevice(c->device));
+  const cudaIpcMemHandle_t* in = (const cudaIpcMemHandle_t*)in208;
+  uint64_t off[2];
+  memcpy(off, (const char*)in208 + 192, sizeof off);
+  MFB_CUDA(cudaIpcOpenMemHandle(&m->map_phi, in[0], cudaIpcMemLazyEnablePeerAccess));
+  if (memcmp(&in[0], &in[1], sizeof in[0]) == 0) {  // phi and bv in one allocation (the arena): one mapping
+    m->map_bv = nullptr;
+    m->peer_bv = (float*)((char*)m->map_phi + off[1]);
+  } else {
+    MFB_CUDA(cudaIpcOpenMemHandle(&m->map_bv, in[1], cudaIpcMemLazyEnablePeerAccess));
+    m->peer_bv = (float*)((char*)m->map_bv + off[1]);
+  }
+  m->peer_phi = (float*)((char*)m->map_phi + off[0]);
+  MFB_CUDA(cudaIpcOpenMemHandle((void**)&m->peer_flags, in[2], cudaIpcMemLazyEnablePeerAccess));
+  m->p2p = true;
+  return MFB_OK;
+}
 
 int mfb_comm_unique_id(void* out128) {
   MFB_REQUIRE(out128, "NULL argument");
@@ -125,6 +244,11 @@ int mfb_comm_destroy(mfb_ctx* h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(m->stream);
   cudaStreamSynchronize(c->stream);
+  if (m->map_phi) cudaIpcCloseMemHandle(m->map_phi);
+  if (m->map_bv) cudaIpcCloseMemHandle(m->map_bv);
+  if (m->peer_flags) cudaIpcCloseMemHandle(m->peer_flags);
+  cudaFree(m->d_flags);
+  cudaFreeHost(m->h_err);
   if (m->nccl) g_nccl.CommDestroy(m->nccl);
   for (cudaEvent_t e : m->marks) cudaEventDestroy(e);
   for (int i = 0; i < MFB_MAX_HALVES; i++) {
@@ -148,6 +272,19 @@ static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb
   const int64_t s0 = bounds[b], s1 = bounds[b + 1], r0 = bounds[nb], r1 = bounds[nb + 1];
   MFB_CUDA(cudaEventRecord(m->computed[slot], c->stream));
   MFB_CUDA(cudaStreamWaitEvent(m->stream, m->computed[slot], 0));
+  if (m->p2p) {
+    // push: the rows this rank has just updated go straight into rank-1's arrays (it is not touching that block: it
+    // works on another one and shipped its previous copy of this one P-1 sub-epochs ago), then the sequence number
+    MFB_CUDA(cudaMemcpyAsync(m->peer_phi + s0 * c->stride, c->arr[MFB_PHI] + s0 * c->stride,
+                             (size_t)(s1 - s0) * c->stride * sizeof(float), cudaMemcpyDefault, m->stream));
+    MFB_CUDA(cudaMemcpyAsync(m->peer_bv + s0, c->arr[MFB_BV] + s0, (size_t)(s1 - s0) * sizeof(float), cudaMemcpyDefault,
+                             m->stream));
+    ring_flag_set_kernel<<<1, 1, 0, m->stream>>>(m->peer_flags + slot, ++m->seq[slot]);
+    MFB_CUDA(cudaGetLastError());
+    m->shift_pending[slot] = true;
+    (void)r0; (void)r1; (void)from;
+    return MFB_OK;
+  }
   MFB_NCCL(g_nccl.GroupStart());
   MFB_NCCL(g_nccl.Send(c->arr[MFB_PHI] + s0 * c->stride, (size_t)(s1 - s0) * c->stride, ncclFloat, to, m->nccl, m->stream));
   MFB_NCCL(g_nccl.Send(c->arr[MFB_BV] + s0, (size_t)(s1 - s0), ncclFloat, to, m->nccl, m->stream));
@@ -159,7 +296,14 @@ static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb
   return MFB_OK;
 }
 static int wait_shift(Context* c, Comm* m, int slot) {
-  if (m->shift_pending[slot]) MFB_CUDA(cudaStreamWaitEvent(c->stream, m->shifted[slot], 0));
+  if (m->shift_pending[slot]) {
+    if (m->p2p) {  // the block rank+1 pushed here: its sequence number equals the count of this rank's own shifts
+      ring_flag_wait_kernel<<<1, 1, 0, c->stream>>>(m->d_flags + slot, m->seq[slot], 10000000000ull, m->d_flags + MFB_MAX_HALVES);
+      MFB_CUDA(cudaGetLastError());
+    } else {
+      MFB_CUDA(cudaStreamWaitEvent(c->stream, m->shifted[slot], 0));
+    }
+  }
   m->shift_pending[slot] = false;
   return MFB_OK;
 }
@@ -188,6 +332,10 @@ int mfb_dsgd_epoch_ex(mfb_ctx* h, const int* datasets, const int32_t* item_bound
   const int P = m->world, H = halves, NB = P * H;
   MFB_REQUIRE(item_bounds[0] == 0 && item_bounds[NB] == c->nv, "item_bounds must span [0, nv] in world*halves blocks");
   MFB_CUDA(cudaSetDevice(c->device));
+  if (m->p2p && m->h_err && *m->h_err) {
+    set_error("DSGD ring: the block of shift %u never arrived from rank %d (10 s)", *m->h_err, (m->rank + 1) % P);
+    return MFB_E_COMM;
+  }
   std::vector<Dataset*> cells(NB);
   bool resident = true;
   for (int j = 0; j < NB; j++) {
@@ -233,6 +381,8 @@ int mfb_dsgd_epoch_ex(mfb_ctx* h, const int* datasets, const int32_t* item_bound
   }
   for (int hh = 0; hh < H; hh++)  // every block is home again before anything else uses the item matrix
     if (int rc = wait_shift(c, m, hh)) return rc;
+  if (m->p2p)  // (checked at the start of the next epoch and by mfb_comm_allreduce_sse)
+    MFB_CUDA(cudaMemcpyAsync(m->h_err, m->d_flags + MFB_MAX_HALVES, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;
   c->model_age++;
@@ -288,6 +438,10 @@ int mfb_comm_allreduce_sse(mfb_ctx* h, double* sse, int64_t* n) {
   MFB_NCCL(g_nccl.AllReduce(m->d_red, m->d_red, 2, ncclDouble, ncclSum, m->nccl, c->stream));
   MFB_CUDA(cudaMemcpyAsync(hb, m->d_red, sizeof hb, cudaMemcpyDeviceToHost, c->stream));
   MFB_CUDA(cudaStreamSynchronize(c->stream));
+  if (m->p2p && m->h_err && *m->h_err) {
+    set_error("DSGD ring: the block of shift %u never arrived from rank %d (10 s)", *m->h_err, (m->rank + 1) % m->world);
+    return MFB_E_COMM;
+  }
   *sse = hb[0];
   *n = (int64_t)(hb[1] + 0.5);
   return MFB_OK;

@@ -91,6 +91,8 @@ SIGNATURES = {
     "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mfb_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mfb_comm_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
     "mfb_dsgd_epoch_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_int]),
@@ -476,6 +478,15 @@ class Context:
     def comm_init(self, rank, world, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _check(lib().mfb_comm_init(self.h, rank, world, buf))
+
+    def comm_ipc_export(self):
+        buf = C.create_string_buffer(208)
+        _check(lib().mfb_comm_ipc_export(self.h, buf))
+        return buf.raw
+
+    def comm_ipc_import(self, handles208):
+        assert len(handles208) == 208
+        _check(lib().mfb_comm_ipc_import(self.h, C.create_string_buffer(handles208, 208)))
 
     def dsgd_epoch(self, datasets, item_bounds, eta, lam, gb, mode=MODE_ATOMIC, halves=1, rotations=1):
         ds = (C.c_int * len(datasets))(*datasets)

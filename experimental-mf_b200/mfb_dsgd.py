@@ -20,6 +20,37 @@ def item_bounds(nv, world):
     return np.array([(nv * j) // world for j in range(world + 1)], np.int32)
 
 
+def balanced_item_map(counts, nblocks, seed=0x4D46B200):
+    """Item blocks of equal cost instead of equal id ranges.  A cell kernel's time is set by its record count AND by the
+    update chain of its most rated item, and a sub-epoch of the ring ends with its slowest cell, so the
+    blocks should hold the same number of records and equally hot hottest items.  Greedy (longest processing time
+    first): the items, most rated first, each go to the block with the fewest records so far - the B most rated items
+    land in B different blocks and the record counts end equal to within one cold item.  Returns (new_of_old[nv] int32,
+    bounds[nblocks+1] int32): the relabelling that makes every block a contiguous id range (the ring ships row ranges
+    of phi / bv) and the ranges.  Inside a block the items are placed by a fixed pseudo-random permutation (hot rows
+    do not sit next to each other in memory).  Deterministic: every rank computes the same map from the same
+    (all-reduced) counts."""
+    import heapq
+    counts = np.asarray(counts, np.int64)
+    nv = len(counts)
+    order = np.argsort(-counts, kind="stable")
+    heap = [(0, b) for b in range(nblocks)]
+    blk_of_rank = np.empty(nv, np.int32)
+    cs = counts[order].tolist()
+    for r in range(nv):
+        load, b = heap[0]
+        blk_of_rank[r] = b
+        heapq.heapreplace(heap, (load + cs[r] + 1, b))   # (+1: items nobody rated still spread evenly)
+    sizes = np.bincount(blk_of_rank, minlength=nblocks)
+    starts = np.r_[0, np.cumsum(sizes)]
+    rng = np.random.default_rng(seed)
+    new_of_old = np.empty(nv, np.int32)
+    for b in range(nblocks):
+        mine = np.nonzero(blk_of_rank == b)[0]
+        new_of_old[order[mine]] = starts[b] + rng.permutation(len(mine))
+    return new_of_old, starts.astype(np.int32)
+
+
 def user_range(nu, rank, world):
     return (nu * rank) // world, (nu * (rank + 1)) // world
 
@@ -50,12 +81,24 @@ class DsgdWorker:
     """This rank's shard of the model and data on its GPU, plus the NCCL ring."""
 
     def __init__(self, nu, nv, k, rank, world, device, train, test, unique_id, seed=0x4D46B200, merge=False,
-                 halves=None, first_epoch_rotations=None):
+                 halves=None, first_epoch_rotations=None, item_map=None):
+        """item_map = balanced_item_map(global rating counts, world * halves): the item ids of `train` and `test` are
+        relabelled IN PLACE and the blocks are the map's ranges; the model lives in the relabelled order on the GPUs
+        (set_model / get_model translate)."""
         self.rank, self.world, self.nv = rank, world, nv
         self.halves = (HALVES if halves is None else halves) if world > 1 else 1
         self.first_epoch_rotations = (FIRST_EPOCH_ROTATIONS if first_epoch_rotations is None else first_epoch_rotations) \
             if world > 1 else 1
-        self.bounds = item_bounds(nv, world * self.halves)   # pieces
+        self.new_of_old = None
+        if item_map is not None:
+            self.new_of_old, self.bounds = np.asarray(item_map[0], np.int32), np.asarray(item_map[1], np.int32)
+            assert len(self.bounds) == world * self.halves + 1 and len(self.new_of_old) == nv
+            for blocks in (train, test):
+                if blocks.nratings:
+                    v = blocks.vid
+                    v[:] = self.new_of_old[v]
+        else:
+            self.bounds = item_bounds(nv, world * self.halves)   # pieces
         self.home_bounds = self.bounds[::self.halves]        # blocks (one per rank)
         self.ctx = mb.Context(nu, nv, k, device)
         self.ctx.init_normal(seed, 1e-2)  # counter-based: identical on every rank
@@ -85,6 +128,45 @@ class DsgdWorker:
         self.epochs_done += 1
         return rotations
 
+    def enable_peer_ring(self):
+        """Ring shifts through peer memory instead of ncclSend/ncclRecv (mfb_comm_ipc_*): every rank's IPC handles are
+        all-gathered with torch.distributed and each rank maps those of the rank it sends to.  Collective: all ranks
+        call it or none.  Returns False (on every rank) when any rank cannot export yet - the placement search may
+        still move its item matrix."""
+        import torch
+        import torch.distributed as dist
+        if self.world < 2:
+            return False
+        try:
+            mine, ok = self.ctx.comm_ipc_export(), 1
+        except mb.MfbError:
+            mine, ok = bytes(208), 0
+        t = torch.frombuffer(bytearray(mine + bytes([ok])), dtype=torch.uint8).cuda()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        out = [bytes(x.cpu().numpy().tobytes()) for x in out]
+        if not all(x[208] for x in out):
+            return False
+        self.ctx.comm_ipc_import(out[(self.rank - 1) % self.world][:208])
+        dist.barrier()  # nobody pushes before every mapping exists
+        return True
+
+    def set_model(self, theta, phi, bu, bv):
+        """factors in the ORIGINAL item order"""
+        if self.new_of_old is not None:
+            p2, b2 = np.empty_like(phi), np.empty_like(bv)
+            p2[self.new_of_old] = phi
+            b2[self.new_of_old] = bv
+            phi, bv = p2, b2
+        self.ctx.set_factors(theta, phi, bu, bv)
+
+    def get_model(self):
+        """factors in the ORIGINAL item order (this rank's copy: call allgather first for the other ranks' blocks)"""
+        theta, phi, bu, bv = self.ctx.get_factors()
+        if self.new_of_old is not None:
+            phi, bv = phi[self.new_of_old], bv[self.new_of_old]
+        return theta, phi, bu, bv
+
     def refresh_from_host(self):
         for ds, b in zip(self.cell_ds, self.cells):
             self.ctx.dataset_refresh_from_host(ds, b)
@@ -97,6 +179,15 @@ class DsgdWorker:
 
     def close(self):
         self.ctx.close()
+
+
+def global_item_map(tr, nv, nblocks):
+    """balanced_item_map over the rating counts of ALL ranks (one all-reduce of nv int64)"""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.from_numpy(np.bincount(np.asarray(tr.vid), minlength=nv).astype(np.int64)).cuda()
+    dist.all_reduce(cnt)
+    return balanced_item_map(cnt.cpu().numpy(), nblocks)
 
 
 def yahoo_subrecord(args, rank, world, local, stream, timed):
@@ -113,7 +204,9 @@ def yahoo_subrecord(args, rank, world, local, stream, timed):
     u0, u1 = user_range(nu, rank, world)
     t0 = time.time()
     tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=test_frac, user_begin=u0, user_end=u1))
-    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, bytes(uid.cpu().numpy().tobytes()))
+    balance = bool(int(os.environ.get("MFB_DSGD_BALANCE", "1")))
+    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, bytes(uid.cpu().numpy().tobytes()),
+                   item_map=global_item_map(tr, nv, world * HALVES) if balance else None)
     w.ctx.set_stream(stream.cuda_stream)
     setup_s = time.time() - t0
     tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda")
@@ -121,6 +214,7 @@ def yahoo_subrecord(args, rank, world, local, stream, timed):
     ntrain = int(tot[0])
     w.ctx.dsgd_epoch(w.cell_ds, w.bounds, 0.0, 0.0, GB, mb.MODE_ATOMIC, w.halves, 1)  # connections, placement
     torch.cuda.synchronize()
+    peer_ring = bool(int(os.environ.get("MFB_DSGD_P2P", "1"))) and w.enable_peer_ring()
     epoch = [0]
 
     def step():
@@ -139,6 +233,7 @@ def yahoo_subrecord(args, rank, world, local, stream, timed):
             "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
             "test_rmse_after_%d_epochs" % epoch[0]: float(np.sqrt(sse / max(n, 1))),
             "first_epoch_ring_turns": w.first_epoch_rotations, "launch": shape, "setup_s": round(setup_s, 1),
+            "exchange": "peer memory (CUDA IPC) + device-side flag" if peer_ring else "ncclSend/ncclRecv",
             "rank0_timeline_ms_wait_kernel": timeline,
             "note": "compare with configs.C5_yahoo_mf_k128_1gpu of the N = 1 line (same data, same epochs, one GPU)"}
 
@@ -161,7 +256,10 @@ def bench(args, wl, shape, rank, world, local, config):
     t0 = time.time()
     tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=test_frac, user_begin=u0, user_end=u1))
     gen_s = time.time() - t0
-    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, unique_id, merge=bool(int(os.environ.get("MFB_DSGD_MERGE", "0"))))
+    balance = bool(int(os.environ.get("MFB_DSGD_BALANCE", "1")))
+    item_map = global_item_map(tr, nv, world * HALVES) if balance else None
+    w = DsgdWorker(nu, nv, k, rank, world, local, tr, te, unique_id, merge=bool(int(os.environ.get("MFB_DSGD_MERGE", "0"))),
+                   item_map=item_map)
     stream = torch.cuda.current_stream()
     w.ctx.set_stream(stream.cuda_stream)
     mode = {"hogwild": mb.MODE_HOGWILD, "atomic": mb.MODE_ATOMIC}[args.schedule]
@@ -171,7 +269,7 @@ def bench(args, wl, shape, rank, world, local, config):
     model = mb.seeded_model(nu, nv, k, g["model_seed"] if g else 20261018)  # the same on every rank
 
     def restart():
-        w.ctx.set_factors(*model)
+        w.set_model(*model)
         w.epochs_done = 0
         epoch[0] = 0
 
@@ -202,6 +300,8 @@ def bench(args, wl, shape, rank, world, local, config):
     # first send/recv (~0.8 s) and the library searches the placement of the item matrix on the first epoch
     w.ctx.dsgd_epoch(w.cell_ds, w.bounds, 0.0, 0.0, GB, mode, w.halves, 1)
     torch.cuda.synchronize()
+    # from here on the ring shifts go through peer memory (NVLink stores into the neighbour's HBM + a device-side flag)
+    peer_ring = bool(int(os.environ.get("MFB_DSGD_P2P", "1"))) and w.enable_peer_ring()
 
     # ---- parity with the reference's own single-thread trajectory: same data, same seeded model ---------------
     parity = None
@@ -303,7 +403,12 @@ def bench(args, wl, shape, rank, world, local, config):
             "dsgd": {"cells_per_rank": world * w.halves, "pieces_per_block": w.halves,
                      "first_epoch_ring_turns": w.first_epoch_rotations,
                      "item_block_bytes": int((nv // world) * mb.lib().mfb_padding(k) * 4),
-                     "exchange": "ncclSend/ncclRecv ring shift of one item block per sub-epoch on a communication stream",
+                     "item_blocks": "equal cost: items dealt over the blocks in serpentine order of their rating count "
+                                    "(mfb_dsgd.balanced_item_map)" if balance else "equal id ranges",
+                     "exchange": ("peer memory: the block is copied straight into the ring neighbour's HBM over NVLink (CUDA IPC "
+                                  "mapping) and a sequence number is raised there; the neighbour's compute stream waits for it "
+                                  "on the device" if peer_ring else
+                                  "ncclSend/ncclRecv ring shift of one item block per sub-epoch on a communication stream"),
                      "rank0_timeline_ms_wait_kernel": timeline},
             "configs": {"C5_yahoo_mf_k128": c5} if c5 else None,
         }

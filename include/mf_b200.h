@@ -266,6 +266,14 @@ int mfb_blocks_regroup(const mfb_blocks* b, int merge_users, int longest_first, 
 int mfb_comm_unique_id(void* out128);
 int mfb_comm_init(mfb_ctx* ctx, int rank, int world, const void* id128);
 int mfb_comm_destroy(mfb_ctx* ctx);
+/* Peer-memory ring (optional; without it the shifts are ncclSend/ncclRecv).  export: three CUDA IPC handles (3 x 64
+ * bytes) of the allocations holding this rank's phi, bv and arrival flags plus the two byte offsets of phi and bv
+ * inside them (208 bytes in all); the host program hands them to rank+1 (any transport), which calls
+ * import with the handles of the rank it sends to (rank-1).  From then on a shift is one copy per array straight into
+ * the neighbour's HBM over NVLink plus a sequence number the neighbour's compute stream waits for on the device.
+ * export fails while the placement search may still relocate the item matrix. */
+int mfb_comm_ipc_export(mfb_ctx* ctx, void* out208);
+int mfb_comm_ipc_import(mfb_ctx* ctx, const void* in208);
 int mfb_dsgd_epoch(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
                    float gb, int mode);
 /* The general form.  halves = H >= 1: every rank's item block is cut into H pieces (item_bounds has world*H+1

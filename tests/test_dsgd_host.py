@@ -157,3 +157,26 @@ def test_regroup_with_a_length_threshold_moves_only_the_long_runs():
     assert (lens[:nlong] >= thr).all() and (np.diff(lens[:nlong]) <= 0).all() and (lens[nlong:] < thr).all()
     # the short runs keep their file order
     np.testing.assert_array_equal(g.run_uid[nlong:], tr.run_uid[lens0 < thr])
+
+
+def test_balanced_item_map_is_a_permutation_with_equal_blocks_and_equal_hottest_items():
+    """mfb_dsgd.balanced_item_map: every block gets the same number of records (to a few percent), one of the B most
+    rated items each, contiguous id ranges; deterministic"""
+    rng = np.random.default_rng(5)
+    nv, B = 1003, 8
+    counts = (1e6 / (1 + np.arange(nv)) ** 0.8).astype(np.int64)[rng.permutation(nv)]
+    new, bounds = mfb_dsgd.balanced_item_map(counts, B)
+    new2, bounds2 = mfb_dsgd.balanced_item_map(counts.copy(), B)
+    np.testing.assert_array_equal(new, new2)
+    np.testing.assert_array_equal(bounds, bounds2)
+    assert sorted(new.tolist()) == list(range(nv))                      # a permutation
+    assert bounds[0] == 0 and bounds[-1] == nv and np.all(np.diff(bounds) > 0)
+    blk = np.searchsorted(bounds, new, side="right") - 1
+    mass = np.bincount(blk, weights=counts, minlength=B)
+    assert mass.max() / mass.min() < 1.01
+    top = np.argsort(-counts)[:B]
+    assert sorted(blk[top].tolist()) == list(range(B))                  # the B hottest items: one per block
+    hottest = np.array([counts[blk == b].max() for b in range(B)])
+    naive = np.array([counts[(nv * b) // B:(nv * (b + 1)) // B].sum() for b in range(B)])
+    assert mass.max() / mass.mean() <= naive.max() / naive.mean() + 1e-9
+    assert hottest.max() == counts.max()

@@ -42,6 +42,35 @@ def test_world_size_one_ring_equals_plain_epoch():
     c.close()
 
 
+def test_relabelled_item_blocks_leave_the_result_unchanged():
+    """balanced_item_map relabels the items (blocks of equal cost as contiguous id ranges); with one rank the schedule
+    is the file order either way, so the ordered epoch must give the same factors bit for bit in the ORIGINAL item
+    order (set_model / get_model translate), and the same test SSE"""
+    nu, nv, dim = 500, 200, 32
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, 30000, test_frac=0.1, users_per_block=50))
+    tr2, te2, _ = mb.generate(mb.gen_params(nu, nv, 30000, test_frac=0.1, users_per_block=50))
+    m = ol.Model(nu, nv, dim, seed=1)
+    th, ph = m.dense()
+    counts = np.bincount(np.asarray(tr.vid), minlength=nv)
+    imap = mfb_dsgd.balanced_item_map(counts, 1)
+    old_vid = np.asarray(tr2.vid).copy()
+    w = mfb_dsgd.DsgdWorker(nu, nv, dim, 0, 1, 0, tr2, te2, mb.comm_unique_id(), item_map=imap)
+    np.testing.assert_array_equal(np.asarray(tr2.vid), imap[0][old_vid])   # relabelled in place
+    w.set_model(th, ph, m.bu, m.bv)
+    c = ctx_from_model(m)
+    d = c.dataset_from_blocks(tr)
+    for ep in (1, 2):
+        w.epoch(mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
+        c.sgd_epoch(d, mb.seteta(2e-2, ep, 1.0), 5e-3, GB, mb.MODE_ORDERED)
+    for a, b in zip(w.get_model(), c.get_factors()):
+        np.testing.assert_array_equal(a, b)
+    s, n = w.global_sse(GB)
+    s2, n2 = c.sse(c.dataset_from_blocks(te), GB)
+    assert n == n2 and abs(s - s2) <= 1e-9 * s2
+    w.close()
+    c.close()
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_cell_schedule_on_one_gpu_equals_oracle_schedule(world):
     nu, nv, dim = 600, 240, 32
@@ -66,10 +95,12 @@ def test_cell_schedule_on_one_gpu_equals_oracle_schedule(world):
     c.close()
 
 
-def test_multi_rank_ring_is_bit_exact_with_the_oracle_walking_the_same_schedule():
-    """The real thing, on every visible GPU pair: one process per GPU, ordered cells, half-block shifts over
-    NCCL overlapped with the other half's kernel, three ring turns in epoch 1 - the factors of every rank must
-    equal the CPU oracle walking the same schedule of pieces, bit for bit (tools/dsgd_check.py exits 1 if not)."""
+@pytest.mark.parametrize("variant", ["nccl", "peer-memory+balanced"])
+def test_multi_rank_ring_is_bit_exact_with_the_oracle_walking_the_same_schedule(variant):
+    """The real thing, on every visible GPU pair: one process per GPU, ordered cells, half-block shifts overlapped
+    with the other half's kernel, three ring turns in epoch 1 - the factors of every rank must equal the CPU oracle
+    walking the same schedule of pieces, bit for bit (tools/dsgd_check.py exits 1 if not).  Once with ncclSend/ncclRecv
+    and equal id ranges, once with the peer-memory ring (CUDA IPC + device-side flags) and blocks of equal cost."""
     out = subprocess.run([sys.executable, "-c", "import torch; print(torch.cuda.device_count())"], capture_output=True, text=True)
     n = int(out.stdout.strip() or 0)
     if n < 2:
@@ -78,7 +109,9 @@ def test_multi_rank_ring_is_bit_exact_with_the_oracle_walking_the_same_schedule(
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tools", "dsgd_check.py")],
-                         capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+                         capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1", PEER="0" if variant == "nccl" else "1",
+                                  BALANCE="0" if variant == "nccl" else "1"))
     print(out.stdout[-3000:])
     assert out.returncode == 0, out.stderr[-3000:]
     assert "bit-exact vs oracle schedule walk: True" in out.stdout

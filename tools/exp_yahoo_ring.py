@@ -14,7 +14,7 @@ nu, nv, nnz, k, tf = WORKLOADS[os.environ.get("WL", "yahoo")]
 u0, u1 = mfb_dsgd.user_range(nu, rank, world)
 tr, te, _ = mb.generate(mb.gen_params(nu, nv, nnz, test_frac=tf, user_begin=u0, user_end=u1))
 stream = torch.cuda.current_stream()
-for halves in [int(x) for x in os.environ.get("HALVES", "1,2").split(",")]:
+for halves, p2p in [(int(x), int(y)) for x in os.environ.get("HALVES", "1").split(",") for y in os.environ.get("P2P", "0,1").split(",")]:
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(mb.comm_unique_id()), dtype=torch.uint8))
@@ -23,6 +23,7 @@ for halves in [int(x) for x in os.environ.get("HALVES", "1,2").split(",")]:
     w.ctx.set_stream(stream.cuda_stream)
     w.ctx.dsgd_epoch(w.cell_ds, w.bounds, 0.0, 0.0, GB, mb.MODE_ATOMIC, w.halves, 1)
     torch.cuda.synchronize()
+    peer = bool(p2p) and w.enable_peer_ring()
     ms = []
     for ep in range(1, 9):
         torch.cuda.synchronize(); dist.barrier()
@@ -34,8 +35,8 @@ for halves in [int(x) for x in os.environ.get("HALVES", "1,2").split(",")]:
     sse, n = w.global_sse(GB)
     tot = torch.tensor([w.ntrain], dtype=torch.int64, device="cuda"); dist.all_reduce(tot)
     if rank == 0:
-        print("halves %d: ms/epoch %s -> %.2f G updates/s (epochs 4-8); tRMSE %.4f; rank-0 waits %.2f ms kernels %.2f ms | %s" % (
-            halves, " ".join("%.1f" % x for x in ms), int(tot[0]) * 5 / sum(ms[3:]) / 1e6, np.sqrt(sse / n), sum(tl[0::2]), sum(tl[1::2]),
+        print("halves %d peer-memory ring %s: ms/epoch %s -> %.2f G updates/s (epochs 4-8); tRMSE %.4f; rank-0 waits %.2f ms kernels %.2f ms | %s" % (
+            halves, peer, " ".join("%.1f" % x for x in ms), int(tot[0]) * 5 / sum(ms[3:]) / 1e6, np.sqrt(sse / n), sum(tl[0::2]), sum(tl[1::2]),
             w.ctx.last_launch()), flush=True)
     w.close()
 dist.destroy_process_group()
