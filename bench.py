@@ -500,6 +500,24 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
             ms.append(c.last_kernel_ms())
         rm = c.rmse(dte, GB)
         shape = c.last_launch()
+        # end to end from pinned host memory: item ids beyond 65,535, so the records travel as 8 bytes, not as 3
+        e2e = None
+        try:
+            try_.pin()
+            secs, h0 = [], c.h2d_bytes()
+            for ep in range(len(ms) + 1, len(ms) + 4):
+                c.sync()
+                t0 = time.perf_counter()
+                c.sgd_epoch_from_host(d, try_, mb.seteta(ETA0, ep, GAM), LAMBDA, GB, mb.MODE_ATOMIC, args.chunk)
+                c.sse(dte, GB)
+                secs.append(time.perf_counter() - t0)
+            e2e = {"value": try_.nratings / min(secs[1:]), "unit": UNIT, "ms_per_step": 1e3 * min(secs[1:]),
+                   "h2d_bytes_per_step": (c.h2d_bytes() - h0) // 3, "d2h_bytes_per_step": 8,
+                   "what": "mfb_sgd_epoch_from_host + mfb_sse, 8-byte records (624,961 items do not fit the 16-bit ids of the "
+                           "packed form): the PCIe copy of 2.0 GB per epoch is the bound"}
+            try_.unpin()
+        except Exception as e:
+            e2e = {"error": "%s: %s" % (type(e).__name__, e)}
         c.close()
         kms = sum(ms[args.warmup:]) / len(ms[args.warmup:])
         peak = measured_peak()[0]
@@ -516,7 +534,7 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
                                      "in registers for a run, part of the 320 MB item matrix is served by the 126 MB L2): this "
                                      "shape reads and writes DRAM at a fifth of its bandwidth - the L2 atomic path binds here too "
                                      "(busiest slice's atomic unit 76 % busy, profiles/r2_sgd_stream_yahoo.md)"},
-                "test_rmse_after_%d_epochs" % len(ms): rm}
+                "e2e": e2e, "test_rmse_after_%d_epochs" % len(ms): rm}
 
     if args.yahoo:
         guarded("C5_yahoo_mf_k128_1gpu", yahoo)
