@@ -489,6 +489,8 @@ int mfb_set_option(mfb_ctx* h, const char* name, int value) {
     c->opt_phi_planes = value;
   } else if (!strcmp(name, "two_streams")) {
     c->opt_two_streams = value != 0;
+  } else if (!strcmp(name, "ring_peer")) {
+    c->opt_ring_peer = value != 0;
   } else if (!strcmp(name, "sgld_flat")) {
     c->opt_sgld_flat = value;
   } else if (!strcmp(name, "file_decode")) {

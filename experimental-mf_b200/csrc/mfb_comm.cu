@@ -93,6 +93,16 @@ struct Comm {
   int nmarks = 0;
 };
 
+static void close_peer(Comm* m) {
+  if (m->map_phi) cudaIpcCloseMemHandle(m->map_phi);
+  if (m->map_bv) cudaIpcCloseMemHandle(m->map_bv);
+  if (m->peer_flags) cudaIpcCloseMemHandle(m->peer_flags);
+  m->map_phi = m->map_bv = nullptr;
+  m->peer_phi = m->peer_bv = nullptr;
+  m->peer_flags = nullptr;
+  m->p2p = false;
+}
+
 // base and size of the cudaMalloc allocation that holds p
 static bool cuda_range(const void* p, void** base, size_t* size) {
   typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
@@ -181,6 +191,21 @@ int mfb_comm_ipc_export(mfb_ctx* h, void* out208) {
   return MFB_OK;
 }
 
+// Unmaps the neighbour's memory (the ring falls back to ncclSend/ncclRecv).  CUDA wants every importer to have closed
+// its mapping before the exporter frees the memory: the host program calls this on all ranks, synchronises them, and
+// only then destroys the contexts (mfb_dsgd.DsgdWorker.close).
+int mfb_comm_ipc_close(mfb_ctx* h) {
+  MFB_REQUIRE(h, "ctx is NULL");
+  Context* c = &h->c;
+  Comm* m = (Comm*)c->comm;
+  if (!m) return MFB_OK;
+  MFB_CUDA(cudaSetDevice(c->device));
+  MFB_CUDA(cudaStreamSynchronize(m->stream));  // this rank's last pushes
+  MFB_CUDA(cudaStreamSynchronize(c->stream));
+  close_peer(m);
+  return MFB_OK;
+}
+
 // in208 = what rank-1 (the rank this one sends to) exported.  From here on the ring shifts go through peer memory.
 int mfb_comm_ipc_import(mfb_ctx* h, const void* in208) {
   MFB_REQUIRE(h && in208, "NULL argument");
@@ -244,9 +269,7 @@ int mfb_comm_destroy(mfb_ctx* h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(m->stream);
   cudaStreamSynchronize(c->stream);
-  if (m->map_phi) cudaIpcCloseMemHandle(m->map_phi);
-  if (m->map_bv) cudaIpcCloseMemHandle(m->map_bv);
-  if (m->peer_flags) cudaIpcCloseMemHandle(m->peer_flags);
+  close_peer(m);
   cudaFree(m->d_flags);
   cudaFreeHost(m->h_err);
   if (m->nccl) g_nccl.CommDestroy(m->nccl);
@@ -272,7 +295,7 @@ static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb
   const int64_t s0 = bounds[b], s1 = bounds[b + 1], r0 = bounds[nb], r1 = bounds[nb + 1];
   MFB_CUDA(cudaEventRecord(m->computed[slot], c->stream));
   MFB_CUDA(cudaStreamWaitEvent(m->stream, m->computed[slot], 0));
-  if (m->p2p) {
+  if (m->p2p && c->opt_ring_peer) {
     // push: the rows this rank has just updated go straight into rank-1's arrays (it is not touching that block: it
     // works on another one and shipped its previous copy of this one P-1 sub-epochs ago), then the sequence number
     MFB_CUDA(cudaMemcpyAsync(m->peer_phi + s0 * c->stride, c->arr[MFB_PHI] + s0 * c->stride,
@@ -297,7 +320,7 @@ static int shift_block(Context* c, Comm* m, const int32_t* bounds, int b, int nb
 }
 static int wait_shift(Context* c, Comm* m, int slot) {
   if (m->shift_pending[slot]) {
-    if (m->p2p) {  // the block rank+1 pushed here: its sequence number equals the count of this rank's own shifts
+    if (m->p2p && c->opt_ring_peer) {  // the block rank+1 pushed here: its sequence number equals the count of this rank's own shifts
       ring_flag_wait_kernel<<<1, 1, 0, c->stream>>>(m->d_flags + slot, m->seq[slot], 10000000000ull, m->d_flags + MFB_MAX_HALVES);
       MFB_CUDA(cudaGetLastError());
     } else {
@@ -381,7 +404,7 @@ int mfb_dsgd_epoch_ex(mfb_ctx* h, const int* datasets, const int32_t* item_bound
   }
   for (int hh = 0; hh < H; hh++)  // every block is home again before anything else uses the item matrix
     if (int rc = wait_shift(c, m, hh)) return rc;
-  if (m->p2p)  // (checked at the start of the next epoch and by mfb_comm_allreduce_sse)
+  if (m->p2p && c->opt_ring_peer)  // (checked at the start of the next epoch and by mfb_comm_allreduce_sse)
     MFB_CUDA(cudaMemcpyAsync(m->h_err, m->d_flags + MFB_MAX_HALVES, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;

@@ -128,6 +128,8 @@ struct Context {
   bool planes_allowed = false;  // set around launches that own the item matrix alone (mfb_sgd_epoch, calibration)
   float* d_phi_planes = nullptr;  // scratch copy in plane layout; lives in the placement arena once the search ran
   int opt_two_streams = 1;      // streamed epochs: alternate chunk kernels over two streams at half width
+  int opt_ring_peer = 1;        // DSGD ring: use the peer-memory mapping once mfb_comm_ipc_import has set it up (0 = stay with
+                                // ncclSend/ncclRecv: the host program clears it on EVERY rank when any rank failed to map)
   int opt_sgld_flat = 1;        // dpmf, parallel schedule: 1 = sub-warp kernel (sgld_flat_kernel), 0 = warp per run (round 1),
                                 // 2 = sub-warp kernel with 8 lanes x 4 float4 at k = 128 (experiment)
   int opt_file_decode = 1;      // out-of-core epoch (mfb_file_epoch.cu): 1 = the raw bytes of the file go to the GPU and

@@ -93,6 +93,7 @@ SIGNATURES = {
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
     "mfb_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfb_comm_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mfb_comm_ipc_close": (C.c_int, [C.c_void_p]),
     "mfb_dsgd_epoch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_float, C.c_float, C.c_float, C.c_int]),
     "mfb_dsgd_epoch_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), i32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_int]),
@@ -487,6 +488,9 @@ class Context:
     def comm_ipc_import(self, handles208):
         assert len(handles208) == 208
         _check(lib().mfb_comm_ipc_import(self.h, C.create_string_buffer(handles208, 208)))
+
+    def comm_ipc_close(self):
+        _check(lib().mfb_comm_ipc_close(self.h))
 
     def dsgd_epoch(self, datasets, item_bounds, eta, lam, gb, mode=MODE_ATOMIC, halves=1, rotations=1):
         ds = (C.c_int * len(datasets))(*datasets)

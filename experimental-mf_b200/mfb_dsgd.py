@@ -145,10 +145,18 @@ class DsgdWorker:
         out = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(out, t)
         out = [bytes(x.cpu().numpy().tobytes()) for x in out]
-        if not all(x[208] for x in out):
+        good = all(x[208] for x in out)
+        if good:
+            try:
+                self.ctx.comm_ipc_import(out[(self.rank - 1) % self.world][:208])
+            except mb.MfbError:
+                good = False
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # (also: nobody pushes before every mapping exists)
+        if not int(flag[0]):
+            self.ctx.set_option("ring_peer", 0)  # some rank could not map its neighbour: everybody stays with NCCL
             return False
-        self.ctx.comm_ipc_import(out[(self.rank - 1) % self.world][:208])
-        dist.barrier()  # nobody pushes before every mapping exists
+        self.peer_ring = True
         return True
 
     def set_model(self, theta, phi, bu, bv):
@@ -178,6 +186,12 @@ class DsgdWorker:
         return self.ctx.allreduce_sse(s, n)
 
     def close(self):
+        if getattr(self, "peer_ring", False):
+            # every importer unmaps before any exporter frees (collective, like enable_peer_ring)
+            import torch.distributed as dist
+            self.ctx.comm_ipc_close()
+            dist.barrier()
+            self.peer_ring = False
         self.ctx.close()
 
 

@@ -274,6 +274,9 @@ int mfb_comm_destroy(mfb_ctx* ctx);
  * export fails while the placement search may still relocate the item matrix. */
 int mfb_comm_ipc_export(mfb_ctx* ctx, void* out208);
 int mfb_comm_ipc_import(mfb_ctx* ctx, const void* in208);
+/* unmap the neighbour's memory again; call on every rank and synchronise the ranks BEFORE any of them destroys its
+ * context (CUDA: an importer must close its mapping before the exporter frees the memory) */
+int mfb_comm_ipc_close(mfb_ctx* ctx);
 int mfb_dsgd_epoch(mfb_ctx* ctx, const int* datasets, const int32_t* item_bounds, float eta, float lambda,
                    float gb, int mode);
 /* The general form.  halves = H >= 1: every rank's item block is cut into H pieces (item_bounds has world*H+1
