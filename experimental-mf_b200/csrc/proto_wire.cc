@@ -38,7 +38,7 @@ struct Cursor {
       if (shift < 64) v |= (uint64_t)(b & 0x7F) << shift;
       if (!(b & 0x80)) return v;
       shift += 7;
-      if (shift > 63 + 7) break;
+      if (shift >= 70) break;  // a varint is at most 10 bytes
     }
     ok = false;
     return 0;

@@ -162,6 +162,53 @@ def test_device_decoder_reads_every_valid_encoding_like_the_host_decoder(tmp_pat
         c.close()
 
 
+def test_device_and_host_decoder_agree_on_damaged_files(tmp_path):
+    """fuzz: a valid file with bytes flipped, inserted, removed or cut off.  Whatever the damage, the two decoders
+    must do the same thing - both refuse the file, or both decode it to the same records (checked through an ordered
+    epoch, bit for bit) - and the device decoder must never read or write out of bounds (the run would die)."""
+    rng = np.random.default_rng(77)
+    nu, nv, dim = 200, 300, 16
+    tr, _, _ = mb.generate(mb.gen_params(nu, nv, 6000, test_frac=0.0, users_per_block=15))
+    good = open(tr.write(str(tmp_path / "good.bin")), "rb").read()
+    m = ol.Model(nu, nv, dim, seed=3)
+    outcomes = {"both refuse": 0, "both decode": 0}
+    for trial in range(40):
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 4))):
+            kind, at = rng.integers(0, 4), int(rng.integers(0, len(b)))
+            if kind == 0:
+                b[at] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                b[at:at] = bytes(rng.integers(0, 256, int(rng.integers(1, 6))).astype(np.uint8))
+            elif kind == 2:
+                del b[at:at + int(rng.integers(1, 6))]
+            else:
+                del b[max(at, len(b) - 200):]
+        path = tmp_path / ("fuzz%d.bin" % trial)
+        path.write_bytes(bytes(b))
+        res = []
+        for decode in (1, 0):
+            c = ctx_from_model(m)
+            c.set_option("file_decode", decode)
+            try:
+                n = c.sgd_epoch_from_file(str(path), 0.02, 5e-3, GB, mb.MODE_ORDERED, tile_ratings=1 << 20)
+                res.append((n, [x.copy() for x in c.get_factors()]))
+            except mb.MfbError:
+                res.append(None)
+            c.close()
+        assert (res[0] is None) == (res[1] is None), "trial %d: device %s, host %s" % (
+            trial, "refused" if res[0] is None else "decoded", "refused" if res[1] is None else "decoded")
+        if res[0] is None:
+            outcomes["both refuse"] += 1
+        else:
+            outcomes["both decode"] += 1
+            assert res[0][0] == res[1][0]
+            for a, bb in zip(res[0][1], res[1][1]):
+                np.testing.assert_array_equal(a, bb)
+    print(outcomes)
+    assert outcomes["both refuse"] > 0 and outcomes["both decode"] > 0
+
+
 @DECODERS
 def test_file_epoch_reports_io_and_format_errors(tmp_path, decode):
     c = mb.Context(50, 50, 16)

@@ -14,7 +14,9 @@ print("top item share %.4f, runs %d" % (np.bincount(tr.vid).max() / tr.nratings,
 res = {}
 for name, opts in [("stream", {"kernel": 3}), ("burst span 32", {"kernel": 4, "span_runs": 32}), ("burst span 8", {"kernel": 4, "span_runs": 8}),
                    ("burst span 2", {"kernel": 4, "span_runs": 2}), ("burst span 8 W 42", {"kernel": 4, "span_runs": 8, "max_groups": 42}),
-                   ("burst span 8 W 21", {"kernel": 4, "span_runs": 8, "max_groups": 21})]:
+                   ("burst span 8 W 21", {"kernel": 4, "span_runs": 8, "max_groups": 21}),
+                   ("burst batch 8", {"kernel": 4, "batch": 8}), ("burst depth 2", {"kernel": 4, "depth": 2}),
+                   ("burst batch 8 depth 2", {"kernel": 4, "batch": 8, "depth": 2}), ("default", {})]:
     c = mb.Context(nu, nv, dim); c.set_factors(th, ph, m.bu, m.bv)
     for k, v in opts.items(): c.set_option(k, v)
     dtr, dte = c.dataset_from_blocks(tr), c.dataset_from_blocks(te)
