@@ -736,7 +736,8 @@ def run_b200_arm(args, wl):
                                              "reduction_only_uniform": lp["uniform"]["red_grows_per_s"]},
                     "frac_of_this_files_pattern": upd_per_s / 1e9 / lp["training_file"]["both_grows_per_s"],
                     "dram_gbs": traffic / (kavg * 1e-3) / 1e9 if traffic else None,
-                    "l2_hit_rate": prof.get("l2_hit_rate_pct") if prof else None,
+                    "l2_hit_rate": (float(prof["lts__t_sector_hit_rate.pct"]["value"]) / 100.0
+                                    if prof and "lts__t_sector_hit_rate.pct" in prof else None),
                     "hbm_algorithmic": {"achieved": hbm_alg, "peak": peak, "unit": "GB/s", "frac": hbm_alg / peak,
                                         "peak_source": peak_src, "bytes_per_update": bytes_per_update(k),
                                         "note": "SURVEY 8d's figure (rating record + two factor rows read and written per "
