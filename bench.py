@@ -594,6 +594,7 @@ def run_b200_arm(args, wl):
         parity = {"test_rmse": traj[-1], "test_rmse_reference": ref[-1], "rmse_abs_diff": abs(traj[-1] - ref[-1]),
                   "rmse_max_abs_diff_over_epochs": max(abs(a - b) for a, b in zip(traj, ref)),
                   "rmse_trajectory": traj, "rmse_reference_trajectory": ref,
+                  "epoch_ms": [b - a for a, b in zip([0.0] + cum_ms[:-1], cum_ms)],
                   "epochs_to_rmse": reach, "seconds_to_rmse": cum_ms[reach - 1] * 1e-3 if reach else None,
                   "rmse_target": "reference's tRMSE after epoch %d (%.6f) + %g" % (len(ref), ref[-1], RMSE_TOL),
                   "reference": "oracle/_ref/mf_ref --fly 1 (the reference's own main(), single-thread update order) on the "

@@ -646,7 +646,7 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
     staged[k % 3] = std::async(std::launch::async, stage_host, fp, c->device, fd, chunk_first[k], chunk_first[k + 1], &fp->slot[k % 3]);
   };
   int rc = MFB_OK;
-  // stage B: H2D of the raw bytes and spans, decode kernels, result back - all on the copy stream
+  // stage B: H2D of the raw bytes and spans (copy stream), then the decode kernels and the result back (decode stream)
   auto issue = [&](size_t k) -> int {
     FSlot* s = &fp->slot[k % 3];
     staged[k % 3].get();
