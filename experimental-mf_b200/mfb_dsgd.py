@@ -199,7 +199,9 @@ def global_item_map(tr, nv, nblocks):
     """balanced_item_map over the rating counts of ALL ranks (one all-reduce of nv int64)"""
     import torch
     import torch.distributed as dist
-    cnt = torch.from_numpy(np.bincount(np.asarray(tr.vid), minlength=nv).astype(np.int64)).cuda()
+    cnt = torch.from_numpy(np.bincount(np.asarray(tr.vid), minlength=nv).astype(np.int64))
+    if dist.get_backend() == "nccl":
+        cnt = cnt.cuda()
     dist.all_reduce(cnt)
     return balanced_item_map(cnt.cpu().numpy(), nblocks)
 

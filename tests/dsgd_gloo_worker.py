@@ -20,11 +20,19 @@ NU, NV, NNZ, DIM, GB, EPOCHS = 400, 150, 20000, 16, 2.76, 2
 HALVES, FIRST_EPOCH_ROTATIONS = 2, 3  # pieces per item block; turns of the ring in epoch 1
 
 
-def cell_datasets(rank, world):
-    """this rank's cells, one per piece (world * HALVES of them), and the piece bounds"""
+def shard(rank, world):
     u0, u1 = mfb_dsgd.user_range(NU, rank, world)
-    tr, _, _ = mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.0, users_per_block=40, user_begin=u0, user_end=u1))
+    return mb.generate(mb.gen_params(NU, NV, NNZ, test_frac=0.0, users_per_block=40, user_begin=u0, user_end=u1))[0]
+
+
+def cell_datasets(rank, world, item_map=None):
+    """this rank's cells, one per piece (world * HALVES of them), and the piece bounds; item_map = blocks of equal
+    cost (mfb_dsgd.balanced_item_map): the items are relabelled, the bounds are the map's"""
+    tr = shard(rank, world)
     bounds = mfb_dsgd.item_bounds(NV, world * HALVES)
+    if item_map is not None:
+        tr.vid[:] = item_map[0][tr.vid]
+        bounds = item_map[1]
     return [ol.Dataset(b.block_off, b.run_uid, b.run_off, b.vid, b.rating) for b in tr.split_by_item(bounds)], bounds
 
 
@@ -32,8 +40,11 @@ def main():
     out = sys.argv[1]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    cells, bounds = cell_datasets(rank, world)
-    m = ol.Model(NU, NV, DIM, seed=3)  # same seeded start on every rank
+    item_map = None
+    if int(os.environ.get("BALANCE", "0")):  # the counts of all ranks, all-reduced over gloo
+        item_map = mfb_dsgd.global_item_map(shard(rank, world), NV, world * HALVES)
+    cells, bounds = cell_datasets(rank, world, item_map)
+    m = ol.Model(NU, NV, DIM, seed=3)  # same seeded start on every rank (in the order the ids have NOW)
     mm = m.as_mfo()
     to, frm = (rank - 1) % world, (rank + 1) % world
     for ep in range(1, EPOCHS + 1):

@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 import mfb200 as mb
 import mfb_dsgd
@@ -73,9 +74,10 @@ def test_merge_runs_keeps_every_record_and_file_order_within_a_user():
         np.testing.assert_array_equal(m.rating[lo:hi], cell.rating[cu == u])
 
 
-def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib):
+@pytest.mark.parametrize("balance", [0, 1], ids=["equal id ranges", "blocks of equal cost"])
+def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib, balance):
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", BALANCE=str(balance))
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                     "--master-addr", "127.0.0.1", "--master-port", "29631",
                     os.path.join(here, "dsgd_gloo_worker.py"), str(tmp_path)], check=True, env=env, timeout=300)
@@ -83,8 +85,12 @@ def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib)
     world = 2
     m = ol.Model(w.NU, w.NV, w.DIM, seed=3)
     mm = m.as_mfo()
-    cells = [w.cell_datasets(r, world)[0] for r in range(world)]
     H = w.HALVES
+    item_map = None
+    if balance:  # the workers all-reduce their shards' counts; the whole file gives the same counts
+        whole = mb.generate(mb.gen_params(w.NU, w.NV, w.NNZ, test_frac=0.0, users_per_block=40))[0]
+        item_map = mfb_dsgd.balanced_item_map(np.bincount(np.asarray(whole.vid), minlength=w.NV), world * H)
+    cells = [w.cell_datasets(r, world, item_map)[0] for r in range(world)]
     for ep in range(1, w.EPOCHS + 1):
         eta = mb.seteta(2e-2, ep, 1.0)
         rotations = w.FIRST_EPOCH_ROTATIONS if ep == 1 else 1
@@ -97,7 +103,7 @@ def test_two_rank_gloo_ring_equals_single_process_schedule(tmp_path, oracle_lib)
                 part = cells[r][j].block_range(k0, k1)  # (keep it alive: as_mfo() holds raw pointers)
                 dd = part.as_mfo()
                 oracle_lib.mfo_sgd_epoch(C.byref(mm), C.byref(dd), eta, 5e-3, w.GB)
-    bounds = mfb_dsgd.item_bounds(w.NV, world * H)
+    bounds = item_map[1] if balance else mfb_dsgd.item_bounds(w.NV, world * H)
     for r in range(world):
         got = np.load(tmp_path / ("rank%d.npz" % r))
         u0, u1 = mfb_dsgd.user_range(w.NU, r, world)
