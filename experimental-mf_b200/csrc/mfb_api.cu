@@ -895,7 +895,11 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
   // (tools/exp_launches.py) - so consecutive chunks go to TWO compute streams at half the width
   // each: the tail of one chunk overlaps the body of the next, and the sum of the runs in flight
   // stays within the concurrency bounds.
-  const int64_t max_chunk = chunk_ratings * 6;
+  // (MFB_CHUNK_CAP / MFB_CHUNK_GROW_PCT: experiment knobs for the two constants)
+  const char* env_cap = getenv("MFB_CHUNK_CAP");
+  const char* env_grow = getenv("MFB_CHUNK_GROW_PCT");
+  const int64_t grow_pct = env_grow ? std::max(100, atoi(env_grow)) : 175;
+  const int64_t max_chunk = chunk_ratings * (env_cap ? std::max(1, atoi(env_cap)) : 6);
   begin_timing(c);
   if (!c->stream2) {
     MFB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -927,7 +931,7 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
     int64_t r1 = r0;
     const int64_t o0 = s->h_run_off[r0];
     int64_t want = chunk_ratings;
-    for (size_t g = 0; g < chunk && want < max_chunk; g++) want = want * 7 / 4;
+    for (size_t g = 0; g < chunk && want < max_chunk; g++) want = want * grow_pct / 100;
     want = std::min(want, max_chunk);
     {  // last run whose end is within `want` records (run_off is sorted)
       const int32_t* ro = s->h_run_off.data();
