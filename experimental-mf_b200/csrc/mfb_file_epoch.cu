@@ -774,6 +774,63 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
   return MFB_OK;
 }
 
+// The host half of the device-decode path on its own, no GPU involved: walks the frames of a [u32 size][mf.Block]
+// file and the top-level fields of every Block the way stage_host does, and reports what it found - frames, serialized
+// mf.User messages and the bytes inside them (what the GPU would be handed).  MFB_E_IO on a truncated frame or a
+// malformed Block.  Used by the CPU tests; also a cheap "is this a rating file" check for a caller.
+extern "C" int mfb_wire_index_file(const char* path, int64_t* nframes, int64_t* nusers, int64_t* user_bytes) {
+  MFB_REQUIRE(path && nframes && nusers && user_bytes, "NULL argument");
+  *nframes = *nusers = *user_bytes = 0;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    set_error("cannot open %s", path);
+    return MFB_E_IO;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    set_error("cannot stat %s", path);
+    return MFB_E_IO;
+  }
+  const int64_t size = (int64_t)st.st_size;
+  std::vector<uint8_t> buf;
+  std::vector<int32_t> spans;
+  int rc = MFB_OK;
+  int64_t p = 0;
+  while (size - p >= 4 && rc == MFB_OK) {
+    uint32_t isize;
+    if (pread(fd, &isize, 4, p) != 4) {
+      set_error("%s: read error at offset %lld", path, (long long)p);
+      rc = MFB_E_IO;
+      break;
+    }
+    p += 4;
+    if ((int64_t)isize > size - p) {
+      set_error("%s: truncated frame (%u bytes wanted, %lld left)", path, isize, (long long)(size - p));
+      rc = MFB_E_IO;
+      break;
+    }
+    buf.resize(isize);
+    if (isize && pread(fd, buf.data(), isize, p) != (ssize_t)isize) {
+      set_error("%s: read error at offset %lld", path, (long long)p);
+      rc = MFB_E_IO;
+      break;
+    }
+    spans.clear();
+    if (!walk_block(buf.data(), isize, 0, &spans)) {
+      set_error("%s: malformed mf.Block in frame %lld", path, (long long)*nframes);
+      rc = MFB_E_IO;
+      break;
+    }
+    for (size_t i = 0; i + 1 < spans.size(); i += 2) *user_bytes += spans[i + 1] - spans[i];
+    *nusers += (int64_t)spans.size() / 2;
+    ++*nframes;
+    p += isize;
+  }
+  close(fd);
+  return rc;
+}
+
 extern "C" int mfb_sgd_epoch_from_file(mfb_ctx* h, const char* path, float eta, float lambda, float gb, int mode,
                                        int64_t tile_ratings, int64_t* ratings_out) {
   MFB_REQUIRE(h && path, "NULL argument");

@@ -88,6 +88,7 @@ SIGNATURES = {
     "mfb_blocks_split_by_item": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p)]),
     "mfb_blocks_merge_runs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "mfb_blocks_regroup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mfb_wire_index_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mfb_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -568,6 +569,13 @@ def seeded_model(nu, nv, dim, seed, scale=1e-2):
     bu = rng.standard_normal(nu, dtype=np.float32) * np.float32(scale)
     bv = rng.standard_normal(nv, dtype=np.float32) * np.float32(scale)
     return theta, phi, bu, bv
+
+
+def wire_index_file(path):
+    """(frames, serialized users, bytes inside them) of a [u32][mf.Block] file: the host half of the device decoder"""
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    _check(lib().mfb_wire_index_file(path.encode(), C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def comm_unique_id():

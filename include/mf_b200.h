@@ -188,6 +188,9 @@ int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float e
  * one have been applied.  *ratings (optional) = records processed. */
 int mfb_sgd_epoch_from_file(mfb_ctx* ctx, const char* path, float eta, float lambda, float gb, int mode,
                             int64_t tile_ratings, int64_t* ratings);
+/* the host half of that path alone (no GPU): frames of the file, serialized mf.User messages in them (top-level walk of
+ * every Block, blocks.proto:14-16) and the bytes inside those messages; MFB_E_IO on a truncated frame / malformed Block */
+int mfb_wire_index_file(const char* path, int64_t* nframes, int64_t* nusers, int64_t* user_bytes);
 /* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
  * the next epoch kernel on `ds` waits for the copy.  Used by the multi-GPU end-to-end path. */
 int mfb_dataset_refresh_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src);

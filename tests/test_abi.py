@@ -93,6 +93,40 @@ def test_wire_kat_and_errors(tmp_path):
         mb.Blocks.read(str(tmp_path / "nope.bin"))
 
 
+def test_host_half_of_the_device_decoder_indexes_frames_and_users(tmp_path):
+    """mfb_wire_index_file = the walk the out-of-core epoch does on the host before the bytes go to the GPU: frames by
+    their [u32] headers, one jump per serialized mf.User inside a Block, unknown top-level fields skipped; the counts
+    must equal what the full host decoder finds, and damage to the framing must be reported"""
+    import struct
+    tr, _, _ = mb.generate(mb.gen_params(500, 200, 20000, test_frac=0.0, users_per_block=37))
+    path = tr.write(str(tmp_path / "train.bin"))
+    frames, users, ubytes = mb.wire_index_file(path)
+    assert (frames, users) == (tr.nblocks, tr.nruns)
+    # every user: tag 08 + uid varint, every record >= 9 bytes; the Block adds tag + length per user, the file 4 per frame
+    raw = open(path, "rb").read()
+    assert 9 * tr.nratings + 2 * tr.nruns <= ubytes < len(raw) - 4 * frames - 2 * users + 1
+    # unknown top-level fields (varint, fixed64, bytes, fixed32) and an empty Block between real ones
+    u1 = b"\x08\x07" + b"\x12\x07\x08\x03\x15" + struct.pack("<f", 4.0)
+    u2 = b"\x08\x2a"
+    blk = b"\x10\x05" + b"\x0a" + bytes([len(u1)]) + u1 + b"\x19" + bytes(8) + b"\x22\x02hi" + b"\x0a" + bytes([len(u2)]) + u2 + b"\x2d" + bytes(4)
+    p2 = tmp_path / "odd.bin"
+    p2.write_bytes(struct.pack("<I", len(blk)) + blk + struct.pack("<I", 0) + struct.pack("<I", len(blk)) + blk)
+    assert mb.wire_index_file(str(p2)) == (3, 4, 2 * (len(u1) + len(u2)))
+    b = mb.Blocks.read(str(p2))
+    assert (b.nblocks, b.nruns, b.nratings) == (3, 4, 2)
+    # a user that runs past its Block, a frame that runs past the file, a group wire type, a missing file
+    for name, data in (("usr.bin", struct.pack("<I", 4) + b"\x0a\x20\x08\x01"), ("frame.bin", struct.pack("<I", 99) + blk),
+                       ("group.bin", struct.pack("<I", 2) + b"\x0b\x00")):
+        q = tmp_path / name
+        q.write_bytes(data)
+        with pytest.raises(mb.MfbError):
+            mb.wire_index_file(str(q))
+    with pytest.raises(mb.MfbError):
+        mb.wire_index_file(str(tmp_path / "nope.bin"))
+    (tmp_path / "empty.bin").write_bytes(b"")
+    assert mb.wire_index_file(str(tmp_path / "empty.bin")) == (0, 0, 0)
+
+
 def _varint(v):
     out = bytearray()
     v &= (1 << 64) - 1
