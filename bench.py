@@ -500,7 +500,8 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
             ms.append(c.last_kernel_ms())
         rm = c.rmse(dte, GB)
         shape = c.last_launch()
-        # end to end from pinned host memory: item ids beyond 65,535, so the records travel as 8 bytes, not as 3
+        # end to end from pinned host memory: item ids beyond 65,535, so the packed records take 4 bytes (16 + 8 bits of item
+        # id, 8 bits of rating code) instead of 3
         e2e = None
         try:
             try_.pin()
@@ -511,10 +512,12 @@ def other_configs(mb, np, args, tr, te, device, cores, t_start):
                 c.sgd_epoch_from_host(d, try_, mb.seteta(ETA0, ep, GAM), LAMBDA, GB, mb.MODE_ATOMIC, args.chunk)
                 c.sse(dte, GB)
                 secs.append(time.perf_counter() - t0)
+            h2d_y = (c.h2d_bytes() - h0) // 3
             e2e = {"value": try_.nratings / min(secs[1:]), "unit": UNIT, "ms_per_step": 1e3 * min(secs[1:]),
-                   "h2d_bytes_per_step": (c.h2d_bytes() - h0) // 3, "d2h_bytes_per_step": 8,
-                   "what": "mfb_sgd_epoch_from_host + mfb_sse, 8-byte records (624,961 items do not fit the 16-bit ids of the "
-                           "packed form): the PCIe copy of 2.0 GB per epoch is the bound"}
+                   "h2d_bytes_per_step": h2d_y, "d2h_bytes_per_step": 8,
+                   "record_bytes": round((h2d_y - 8 * try_.nruns) / try_.nratings, 2),
+                   "what": "mfb_sgd_epoch_from_host + mfb_sse; 624,961 items do not fit 16-bit ids: the packed records carry a "
+                           "third id byte (4 bytes per record; 8 when the ratings have more than 256 distinct values)"}
             try_.unpin()
         except Exception as e:
             e2e = {"error": "%s: %s" % (type(e).__name__, e)}

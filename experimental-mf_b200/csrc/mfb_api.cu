@@ -432,6 +432,7 @@ void mfb_destroy(mfb_ctx* h) {
   for (int b = 0; b < 2; b++) {
     cudaFree(c->d_stage_vid[b]);
     cudaFree(c->d_stage_code[b]);
+    cudaFree(c->d_stage_vhi[b]);
   }
   cudaFree(c->d_dict);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
@@ -813,8 +814,10 @@ static int ensure_stage(Context* c, int64_t capacity) {
   for (int b = 0; b < 2; b++) {
     cudaFree(c->d_stage_vid[b]);
     cudaFree(c->d_stage_code[b]);
+    cudaFree(c->d_stage_vhi[b]);
     MFB_CUDA(cudaMalloc(&c->d_stage_vid[b], c->stage_capacity * sizeof(uint16_t)));
     MFB_CUDA(cudaMalloc(&c->d_stage_code[b], c->stage_capacity));
+    MFB_CUDA(cudaMalloc(&c->d_stage_vhi[b], c->stage_capacity));
   }
   if (!c->d_dict) MFB_CUDA(cudaMalloc(&c->d_dict, 256 * sizeof(float)));
   return MFB_OK;
@@ -950,11 +953,14 @@ int mfb_sgd_epoch_from_host(mfb_ctx* h, int ds, const mfb_blocks* src, float eta
                                cudaMemcpyHostToDevice, c->copy_stream));
       MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code + o0, (o1 - o0), cudaMemcpyHostToDevice,
                                c->copy_stream));
+      if (s->p_vhi)
+        MFB_CUDA(cudaMemcpyAsync(c->d_stage_vhi[sb], s->p_vhi + o0, (o1 - o0), cudaMemcpyHostToDevice, c->copy_stream));
       c->stream = c->copy_stream;  // (stream order frees the staging buffer for the copy after next)
-      rc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid + o0, d->d_rating + o0, o1 - o0);
+      rc = launch_unpack(c, c->d_stage_vid[sb], s->p_vhi ? c->d_stage_vhi[sb] : nullptr, c->d_stage_code[sb], c->d_dict,
+                         d->d_vid + o0, d->d_rating + o0, o1 - o0);
       c->stream = main_stream;
       if (rc) break;
-      c->h2d_bytes += (o1 - o0) * 3;
+      c->h2d_bytes += (o1 - o0) * (s->p_vhi ? 4 : 3);
     } else {
       MFB_CUDA(cudaMemcpyAsync(d->d_vid + o0, s->h_vid.data() + o0, (o1 - o0) * sizeof(int32_t),
                                cudaMemcpyHostToDevice, c->copy_stream));
@@ -1023,12 +1029,14 @@ int mfb_dataset_refresh_from_host(mfb_ctx* h, int ds, const mfb_blocks* src) {
     MFB_CUDA(cudaMemcpyAsync(c->d_dict, s->p_dict, 256 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(c->d_stage_vid[sb], s->p_vid, d->nratings * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(c->d_stage_code[sb], s->p_code, d->nratings, cudaMemcpyHostToDevice, c->copy_stream));
+    if (s->p_vhi) MFB_CUDA(cudaMemcpyAsync(c->d_stage_vhi[sb], s->p_vhi, d->nratings, cudaMemcpyHostToDevice, c->copy_stream));
     cudaStream_t const main_stream = c->stream;
     c->stream = c->copy_stream;
-    const int urc = launch_unpack(c, c->d_stage_vid[sb], c->d_stage_code[sb], c->d_dict, d->d_vid, d->d_rating, d->nratings);
+    const int urc = launch_unpack(c, c->d_stage_vid[sb], s->p_vhi ? c->d_stage_vhi[sb] : nullptr, c->d_stage_code[sb], c->d_dict,
+                                  d->d_vid, d->d_rating, d->nratings);
     c->stream = main_stream;
     if (urc) return urc;
-    c->h2d_bytes += d->nratings * 3;
+    c->h2d_bytes += d->nratings * (s->p_vhi ? 4 : 3);
   } else if (d->nratings) {
     MFB_CUDA(cudaMemcpyAsync(d->d_vid, s->h_vid.data(), d->nratings * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
     MFB_CUDA(cudaMemcpyAsync(d->d_rating, s->h_rating.data(), d->nratings * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
@@ -1051,11 +1059,15 @@ int mfb_blocks_pin(mfb_blocks* b) {
   MFB_CUDA(reg(s->h_vid.data(), s->h_vid.size() * sizeof(int32_t)));
   MFB_CUDA(reg(s->h_rating.data(), s->h_rating.size() * sizeof(float)));
   s->pinned = true;
-  // compact form for streaming: u16 item ids + u8 codes into a table of the distinct rating values
+  // compact form for streaming: u16 item ids (+ a u8 plane for bits 16..23 when some id needs them) + u8 codes into
+  // a table of the distinct rating values: 3 (4) bytes per record instead of 8, lossless
   s->packed = false;
   const size_t n = s->h_vid.size();
-  bool fits = n > 0;
-  for (size_t i = 0; fits && i < n; i++) fits = s->h_vid[i] >= 0 && s->h_vid[i] < 65536;
+  bool fits = n > 0, wide = false;
+  for (size_t i = 0; fits && i < n; i++) {
+    fits = s->h_vid[i] >= 0 && s->h_vid[i] < (1 << 24);
+    wide = wide || s->h_vid[i] >= 65536;
+  }
   if (fits) {
     std::vector<uint8_t> code(n);
     int ndict = 0;
@@ -1086,7 +1098,10 @@ int mfb_blocks_pin(mfb_blocks* b) {
     if (fits) {
       MFB_CUDA(cudaHostAlloc((void**)&s->p_vid, n * sizeof(uint16_t), cudaHostAllocPortable));
       MFB_CUDA(cudaHostAlloc((void**)&s->p_code, n, cudaHostAllocPortable));
-      for (size_t i = 0; i < n; i++) s->p_vid[i] = (uint16_t)s->h_vid[i];
+      if (wide) MFB_CUDA(cudaHostAlloc((void**)&s->p_vhi, n, cudaHostAllocPortable));
+      for (size_t i = 0; i < n; i++) s->p_vid[i] = (uint16_t)(s->h_vid[i] & 0xffff);
+      if (wide)
+        for (size_t i = 0; i < n; i++) s->p_vhi[i] = (uint8_t)(s->h_vid[i] >> 16);
       memcpy(s->p_code, code.data(), n);
       s->packed = true;
     }
@@ -1105,8 +1120,10 @@ int mfb_blocks_unpin(mfb_blocks* b) {
   if (s->packed) {
     cudaFreeHost(s->p_vid);
     cudaFreeHost(s->p_code);
+    cudaFreeHost(s->p_vhi);
     s->p_vid = nullptr;
     s->p_code = nullptr;
+    s->p_vhi = nullptr;
     s->packed = false;
   }
   s->pinned = false;

@@ -47,8 +47,9 @@ struct Dataset {
   // compact wire form of vid/rating for host -> device streaming (mfb_blocks_pin builds it when the
   // data allow: item ids below 65536 and at most 256 distinct rating values): 3 bytes per record
   // instead of 8, lossless
-  uint16_t* p_vid = nullptr;   // cudaHostAlloc'ed (page-locked from the start)
+  uint16_t* p_vid = nullptr;   // cudaHostAlloc'ed (page-locked from the start): item id, low 16 bits
   uint8_t* p_code = nullptr;
+  uint8_t* p_vhi = nullptr;    // item id, bits 16..23: only when some id needs them (4 bytes per record instead of 3)
   float p_dict[256] = {0};
   bool packed = false;
   // device SoA tiles
@@ -91,6 +92,7 @@ struct Context {
   // ... packed chunks land in one of two staging buffers and are expanded on the device
   uint16_t* d_stage_vid[2] = {nullptr, nullptr};
   uint8_t* d_stage_code[2] = {nullptr, nullptr};
+  uint8_t* d_stage_vhi[2] = {nullptr, nullptr};
   float* d_dict = nullptr;  // [256]
   int64_t stage_capacity = 0;
   int stage_flip = 0;               // which staging buffer the next packed refresh uses
@@ -217,8 +219,8 @@ int launch_sgd(Context* c, Dataset* d, float eta, float lambda, float gb, int mo
 int launch_sse(Context* c, Dataset* d, float gb, int link = 0);
 int launch_fill_normal(Context* c, uint64_t seed, float scale);
 // expand n packed records (u16 item id, u8 rating code) into the SoA tiles
-int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* code, const float* dict, int32_t* vid,
-                  float* rating, int64_t n);
+int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* vhi, const uint8_t* code, const float* dict,
+                  int32_t* vid, float* rating, int64_t n);  // vhi may be NULL (ids below 65536)
 // kernels (mfb_sgld.cu)
 int launch_sgld(Context* c, Dataset* d, const mfb_sgld_params* p, float gb, int mode);
 int launch_flush(Context* c, Dataset* d, const mfb_sgld_params* p);

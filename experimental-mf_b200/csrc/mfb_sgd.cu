@@ -260,26 +260,28 @@ __global__ void fill_normal_kernel(float* p, int64_t rows, int cols, int stride,
   }
 }
 
-// expand packed records (the compact host form, mfb_blocks_pin): 3 B in, 8 B out per record
-__global__ void unpack_kernel(const uint16_t* __restrict__ vid16, const uint8_t* __restrict__ code,
-                              const float* __restrict__ dict, int32_t* __restrict__ vid,
-                              float* __restrict__ rating, int64_t n) {
+// expand packed records (the compact host form, mfb_blocks_pin): 3 or 4 B in, 8 B out per record
+__global__ void unpack_kernel(const uint16_t* __restrict__ vid16, const uint8_t* __restrict__ vhi,
+                              const uint8_t* __restrict__ code, const float* __restrict__ dict,
+                              int32_t* __restrict__ vid, float* __restrict__ rating, int64_t n) {
   __shared__ float sdict[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sdict[i] = dict[i];
   __syncthreads();
   // streaming loads and stores (evict-first): 11 bytes per record pass through here every epoch and
   // must not push the item matrix out of the L2
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    __stcs(vid + i, (int32_t)__ldcs(vid16 + i));
+    int32_t v = (int32_t)__ldcs(vid16 + i);
+    if (vhi) v |= (int32_t)__ldcs(vhi + i) << 16;
+    __stcs(vid + i, v);
     __stcs(rating + i, sdict[__ldcs(code + i)]);
   }
 }
 
-int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* code, const float* dict, int32_t* vid,
-                  float* rating, int64_t n) {
+int launch_unpack(Context* c, const uint16_t* vid16, const uint8_t* vhi, const uint8_t* code, const float* dict,
+                  int32_t* vid, float* rating, int64_t n) {
   if (n <= 0) return MFB_OK;
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
-  unpack_kernel<<<grid, 256, 0, c->stream>>>(vid16, code, dict, vid, rating, n);
+  unpack_kernel<<<grid, 256, 0, c->stream>>>(vid16, vhi, code, dict, vid, rating, n);
   MFB_CUDA(cudaGetLastError());
   c->launches++;
   return MFB_OK;

@@ -194,9 +194,10 @@ int mfb_wire_index_file(const char* path, int64_t* nframes, int64_t* nusers, int
 /* re-send the tiles of finalized dataset `ds` from the (pinned) arrays of `src` on the copy stream;
  * the next epoch kernel on `ds` waits for the copy.  Used by the multi-GPU end-to-end path. */
 int mfb_dataset_refresh_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src);
-/* pin: registers the arrays with CUDA and, when the data allow (item ids < 65536, at most 256 distinct
- * rating values), builds a lossless compact copy (u16 id + u8 code, 3 bytes per record) that the
- * streamed epoch sends instead of the 8-byte records and expands on the device */
+/* pin: registers the arrays with CUDA and, when the data allow (item ids < 2^24, at most 256 distinct
+ * rating values), builds a lossless compact copy (u16 id + u8 code, 3 bytes per record; a second u8 plane with
+ * bits 16..23 of the id when some id is >= 65536: 4 bytes) that the streamed epoch sends instead of the 8-byte
+ * records and expands on the device */
 int mfb_blocks_pin(mfb_blocks* b);
 int mfb_blocks_unpin(mfb_blocks* b);
 /* MF::calc_mse (model.cc:41-73): SUM of squared errors and the record count. */

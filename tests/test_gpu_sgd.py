@@ -338,16 +338,20 @@ def test_init_normal_statistics():
 
 @pytest.mark.parametrize("packed", [1, 0])
 @pytest.mark.parametrize("fractional", [False, True])
-def test_streamed_epoch_from_host_equals_resident_epoch(packed, fractional):
+@pytest.mark.parametrize("wide", [False, True], ids=["ids below 65536", "ids up to 200000"])
+def test_streamed_epoch_from_host_equals_resident_epoch(packed, fractional, wide):
     """mfb_sgd_epoch_from_host (rating tiles in pinned host memory, copied chunk by chunk behind the
-    kernel; compact 3-byte records when the data allow, else the 8-byte ones) must give what the
-    resident epoch gives.  Conflict-free data, so the parallel schedule is order-independent; ratings
-    with more than 256 distinct values cannot be packed and take the plain path."""
+    kernel; compact records when the data allow - 3 bytes, 4 when an item id needs more than 16 bits -
+    else the 8-byte ones) must give what the resident epoch gives.  Conflict-free data, so the parallel
+    schedule is order-independent; ratings with more than 256 distinct values cannot be packed and take
+    the plain path."""
     n = 30000
+    nv = 200000 if wide else n
     rng = np.random.default_rng(7)
     ratings = rng.random(n).astype(np.float32) * 4 + 1 if fractional else rng.integers(1, 6, n)
-    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1), rng.permutation(n), ratings)
-    m = ol.Model(n, n, 64, seed=3, scale=0.3)
+    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1), rng.permutation(nv)[:n], ratings)
+    assert (ds.vid.max() >= 65536) == wide
+    m = ol.Model(n, nv, 64, seed=3, scale=0.3)
     blocks = mb.Blocks.from_arrays(ds.block_off, ds.run_uid, ds.run_off, ds.vid, ds.rating)
     blocks.pin()
     c1, c2 = ctx_from_model(m), ctx_from_model(m)
@@ -359,7 +363,7 @@ def test_streamed_epoch_from_host_equals_resident_epoch(packed, fractional):
         c2.sgd_epoch_from_host(d2, blocks, eta, 0.02, GB, mb.MODE_ATOMIC, 7000)  # several chunks
     sent = (c2.h2d_bytes() - b0) / 2
     nchunks = 3  # 7,000 + 12,250 + the remaining 10,750 (of 21,437) records: chunks grow x7/4
-    assert sent == n * (3 if packed and not fractional else 8) + n * 8 + 4 * nchunks
+    assert sent == n * ((4 if wide else 3) if packed and not fractional else 8) + n * 8 + 4 * nchunks
     for a, b in zip(c1.get_factors(), c2.get_factors()):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
     oracle_sgd(m, ds, 0.05, 0.02, GB)
