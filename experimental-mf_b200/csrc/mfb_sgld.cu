@@ -667,7 +667,14 @@ int launch_sgld_t(Context* c, const Dataset* d, const SgldArgs& a, int mode) {
     // 16 x 2: 33.1 ms and 37 / 33 ms.  Option sgld_flat = 2 selects 8 x 4.)
     if (a.nvec > 16 && a.nvec <= 32 && c->opt_sgld_flat == 2) return launch_sgld_flat<8, 4>(c, d, a);
     if (a.nvec > 16 && a.nvec <= 32) return launch_sgld_flat<16, 2>(c, d, a);    // k <= 128
-    if (a.nvec > 8 && a.nvec <= 16) return launch_sgld_flat<8, 2>(c, d, a);      // k <= 64
+    if (a.nvec > 8 && a.nvec <= 16) {                                           // k <= 64
+      // four runs per warp (8 x 2) need the fewest instructions per record (20.5 against 21.0 ms) but leave half as
+      // many warps: while the budgets keep the launch narrow (first epochs: 34 / 25 ms against 27 / 21) two runs
+      // per warp (16 x 1) hide latency better
+      const int64_t allowed = bounded_groups(c, (int64_t)c->sm_count * 64, d->max_item_share, d->nruns, 1.0, a.scal);
+      if (c->opt_sgld_flat == 2 || allowed < 6000) return launch_sgld_flat<16, 1>(c, d, a);
+      return launch_sgld_flat<8, 2>(c, d, a);
+    }
     if (a.nvec > 4 && a.nvec <= 8) return launch_sgld_flat<4, 2>(c, d, a);       // k <= 32
   }
   if (mode == MFB_MODE_ORDERED) {
