@@ -162,7 +162,7 @@ int alloc_slot(Slot* s, int64_t cap_ratings, int64_t cap_runs) {
 using namespace mfb;
 
 static int epoch_from_file_device(Context* c, const char* path, float eta, float lambda, float gb, int mode,
-                                  int64_t tile_ratings, int64_t* ratings_out);
+                                  int64_t tile_ratings, int64_t* ratings_out, Dataset* keep = nullptr, bool do_epoch = true);
 
 // the chunks decoded by the host cores (option file_decode = 0; the round-2 path, kept for comparison)
 static int epoch_from_file_host(Context* c, const char* path, float eta, float lambda, float gb, int mode,
@@ -360,6 +360,7 @@ struct FSlot {
   cudaEvent_t copied = nullptr, decode_begin = nullptr, decoded = nullptr, computed = nullptr;
   bool copy_pending = false, decode_pending = false, compute_pending = false;
   // the chunk the host stage left in the pinned buffers
+  std::vector<int64_t> frame_runs;  // serialized users per frame of the chunk (the Blocks of the file)
   int64_t nruns = 0;
   size_t nbytes = 0;
   bool ok = true;
@@ -519,12 +520,14 @@ void stage_host(FilePipe* fp, int device, int fd, size_t f0, size_t f1, FSlot* s
   worker();
   for (auto& t : pool) t.join();
   int64_t runs = 0;
+  s->frame_runs.assign(nf, 0);
   for (size_t i = 0; i < nf; i++) {
     if (!ok[i] && s->ok) {
       s->ok = false;
       s->bad_frame = f0 + i;
     }
-    runs += (int64_t)spans[i].size() / 2;
+    s->frame_runs[i] = (int64_t)spans[i].size() / 2;
+    runs += s->frame_runs[i];
   }
   if (!s->ok) return;
   if (ensure_runs_host(s, runs) != MFB_OK) {
@@ -560,8 +563,28 @@ void free_file_pipe(Context* c) {
 
 }  // namespace mfb
 
+// streaming ingest: the run offsets of a chunk, shifted by the records already kept; per-item counts accumulated
+__global__ void keep_offsets_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int n, int32_t base) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i] + base;
+}
+__global__ void keep_hist_kernel(int32_t* __restrict__ total, const int32_t* __restrict__ chunk, int n) {
+  // (consecutive chunks run on two streams: their additions may meet)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (chunk[i]) atomicAdd(total + i, chunk[i]);
+}
+__global__ void keep_max_kernel(const int32_t* __restrict__ hist, int n, int32_t* out) {
+  int m = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, hist[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// keep != NULL: STREAMING INGEST: what the chunks decode to is also appended to the resident tiles of
+// `keep` (device to device, behind the chunk's update kernel), so that after this one pass over the file the dataset is
+// finalized in HBM - the one-time parse + upload stall of mfb_dataset_load_file / finalize disappears into the first
+// epoch.  do_epoch = false: ingest only (no update kernels).
 static int epoch_from_file_device(Context* c, const char* path, float eta, float lambda, float gb, int mode,
-                                  int64_t tile_ratings, int64_t* ratings_out) {
+                                  int64_t tile_ratings, int64_t* ratings_out, Dataset* keep, bool do_epoch) {
   const int fd = open(path, O_RDONLY);
   if (fd < 0) {
     set_error("cannot open %s", path);
@@ -641,6 +664,31 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
   MFB_CUDA(cudaStreamWaitEvent(fp->decode_stream, fp->start, 0));
   cudaStream_t const main_stream = c->stream;
   const bool two = c->opt_two_streams != 0 && nchunks > 1 && mode != MFB_MODE_ORDERED;
+  // resident tiles of the dataset being ingested: records bounded by bytes / 9 (grown if the file has shorter ones)
+  int64_t keep_runs = 0, keep_recs = 0, cap_keep_runs = 0, cap_keep_recs = 0;
+  int32_t* d_ghist = nullptr;  // [nv + 1]: records per item over the whole file, then their maximum
+  auto grow = [&](void** ptr, size_t elem, int64_t used, int64_t cap, int64_t want) -> int {
+    void* q = nullptr;
+    MFB_CUDA(cudaDeviceSynchronize());  // (rare: kernels of earlier chunks may still read the old array)
+    MFB_CUDA(cudaMalloc(&q, (size_t)want * elem));
+    if (*ptr && used > 0) MFB_CUDA(cudaMemcpy(q, *ptr, (size_t)used * elem, cudaMemcpyDeviceToDevice));
+    (void)cap;
+    cudaFree(*ptr);
+    *ptr = q;
+    return MFB_OK;
+  };
+  if (keep) {
+    cap_keep_recs = size / 9 + 16;
+    cap_keep_runs = std::max<int64_t>(size / 96, 1 << 16);
+    MFB_CUDA(cudaMalloc(&keep->d_vid, cap_keep_recs * sizeof(int32_t)));
+    MFB_CUDA(cudaMalloc(&keep->d_rating, cap_keep_recs * sizeof(float)));
+    MFB_CUDA(cudaMalloc(&keep->d_run_uid, cap_keep_runs * sizeof(int32_t)));
+    MFB_CUDA(cudaMalloc(&keep->d_run_off, (cap_keep_runs + 1) * sizeof(int32_t)));
+    MFB_CUDA(cudaMemsetAsync(keep->d_run_off, 0, sizeof(int32_t), c->stream));
+    MFB_CUDA(cudaMalloc(&d_ghist, ((size_t)c->nv + 1) * sizeof(int32_t)));
+    MFB_CUDA(cudaMemsetAsync(d_ghist, 0, ((size_t)c->nv + 1) * sizeof(int32_t), c->stream));
+    keep->h_block_off.assign(1, 0);
+  }
   std::future<void> staged[3];
   auto stage = [&](size_t k) {
     staged[k % 3] = std::async(std::launch::async, stage_host, fp, c->device, fd, chunk_first[k], chunk_first[k + 1], &fp->slot[k % 3]);
@@ -722,7 +770,52 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
       }
       break;
     }
+    const bool second = two && (k & 1) == 1;
+    cudaStream_t const kstream = second ? c->stream2 : main_stream;  // where this chunk's kernels go
+    if (keep) {
+      // append what the chunk decoded to: user ids, shifted run offsets, records, per-item counts
+      if (keep_runs + s->nruns > cap_keep_runs) {
+        const int64_t want = std::max(keep_runs + s->nruns, 2 * cap_keep_runs);
+        if ((rc = grow((void**)&keep->d_run_uid, sizeof(int32_t), keep_runs, cap_keep_runs, want)) ||
+            (rc = grow((void**)&keep->d_run_off, sizeof(int32_t), keep_runs + 1, cap_keep_runs + 1, want + 1)))
+          break;
+        cap_keep_runs = want;
+      }
+      if (keep_recs + res.nratings > cap_keep_recs) {
+        const int64_t want = std::max<int64_t>(keep_recs + res.nratings, 2 * cap_keep_recs);
+        if ((rc = grow((void**)&keep->d_vid, sizeof(int32_t), keep_recs, cap_keep_recs, want)) ||
+            (rc = grow((void**)&keep->d_rating, sizeof(float), keep_recs, cap_keep_recs, want)))
+          break;
+        cap_keep_recs = want;
+      }
+      if (keep_recs + res.nratings >= (long long)INT32_MAX) {
+        set_error("%s: more than 2^31 records", path);
+        rc = MFB_E_IO;
+        break;
+      }
+      cudaStreamWaitEvent(kstream, s->decoded, 0);
+      if (s->nruns) {
+        cudaMemcpyAsync(keep->d_run_uid + keep_runs, s->d_run_uid, s->nruns * sizeof(int32_t), cudaMemcpyDeviceToDevice, kstream);
+        keep_offsets_kernel<<<(int)std::min<int64_t>((s->nruns + 255) / 256, 1024), 256, 0, kstream>>>(
+            keep->d_run_off + keep_runs + 1, s->d_run_off + 1, (int)s->nruns, (int32_t)keep_recs);
+      }
+      if (res.nratings) {
+        cudaMemcpyAsync(keep->d_vid + keep_recs, s->d_vid, res.nratings * sizeof(int32_t), cudaMemcpyDeviceToDevice, kstream);
+        cudaMemcpyAsync(keep->d_rating + keep_recs, s->d_rating, res.nratings * sizeof(float), cudaMemcpyDeviceToDevice, kstream);
+        keep_hist_kernel<<<(c->nv + 255) / 256, 256, 0, kstream>>>(d_ghist, s->d_hist, c->nv);
+      }
+      c->launches += 2;
+      for (int64_t fr : s->frame_runs) keep->h_block_off.push_back(keep->h_block_off.back() + fr);
+      keep_runs += s->nruns;
+      keep_recs += res.nratings;
+      if (res.nratings == 0 || !do_epoch) {  // no update kernel follows: the slot is free once the copies are done
+        cudaEventRecord(s->computed, kstream);
+        s->compute_pending = true;
+      }
+    }
     if (res.nratings == 0) continue;
+    total_ratings += do_epoch ? 0 : res.nratings;
+    if (!do_epoch) continue;
     bytes_seen += (int64_t)s->nbytes;
     runs_seen += s->nruns;
     const int64_t est_total_runs = (int64_t)((double)runs_seen * (double)size / (double)std::max<int64_t>(bytes_seen, 1));
@@ -735,8 +828,7 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
     view.d_vid = s->d_vid;
     view.d_rating = s->d_rating;
     view.max_item_share = (double)res.top_count / (double)res.nratings;
-    const bool second = two && (k & 1) == 1;
-    c->stream = second ? c->stream2 : main_stream;
+    c->stream = kstream;
     c->counter_slot = second ? 2 : 0;
     c->width_div = two ? 2 : 1;
     cudaError_t e = cudaStreamWaitEvent(c->stream, s->decoded, 0);
@@ -758,15 +850,50 @@ static int epoch_from_file_device(Context* c, const char* path, float eta, float
   cudaStreamWaitEvent(c->stream, c->ev_s2, 0);
   cudaEventRecord(c->ev1, c->stream);
   c->timed = true;
+  if (rc == MFB_OK && keep) {
+    // the dataset is resident: bring the small run tables to the host (epoch slices, DSGD splits and the streamed
+    // epochs read them there) and the share of the most rated item
+    keep_max_kernel<<<1, 1024, 0, c->stream>>>(d_ghist, c->nv, d_ghist + c->nv);
+    int32_t top = 0;
+    keep->h_run_uid.resize((size_t)keep_runs);
+    keep->h_run_off.resize((size_t)keep_runs + 1);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(&top, d_ghist + c->nv, sizeof top, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && keep_runs)
+      e = cudaMemcpy(keep->h_run_uid.data(), keep->d_run_uid, keep_runs * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(keep->h_run_off.data(), keep->d_run_off, (keep_runs + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      set_error("streaming ingest: %s", cudaGetErrorString(e));
+      rc = MFB_E_CUDA;
+    } else {
+      keep->nruns = keep_runs;
+      keep->nratings = keep_recs;
+      keep->nblocks = (int64_t)keep->h_block_off.size() - 1;
+      keep->max_item_share = keep_recs ? (double)top / (double)keep_recs : 0.0;
+      keep->finalized = true;
+    }
+  }
   if (rc != MFB_OK) {  // leave nothing queued on buffers whose content is undefined
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(fp->decode_stream);
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream);
+    cudaFree(d_ghist);
+    if (keep) {  // back to an empty, unfinalized dataset
+      cudaFree(keep->d_vid); cudaFree(keep->d_rating); cudaFree(keep->d_run_uid); cudaFree(keep->d_run_off);
+      keep->d_vid = keep->d_run_uid = keep->d_run_off = nullptr;
+      keep->d_rating = nullptr;
+      keep->h_run_uid.clear();
+      keep->h_run_off.clear();
+      keep->h_block_off.clear();
+      keep->finalized = false;
+    }
     return rc;
   }
-  c->model_age++;
-  if (ratings_out) *ratings_out = total_ratings;
+  cudaFree(d_ghist);
+  if (do_epoch) c->model_age++;
+  if (ratings_out) *ratings_out = keep ? keep_recs : total_ratings;
   if (clock_on)
     fprintf(stderr, "mfb_sgd_epoch_from_file: %zu chunks, %.1f MB: host thread %.1f ms = %.1f waiting for the pread/walk stage "
             "+ %.1f waiting for copy+decode + %.1f launching; decode kernels %.1f ms on the device\n", nchunks, size / 1e6,
@@ -842,4 +969,38 @@ extern "C" int mfb_sgd_epoch_from_file(mfb_ctx* h, const char* path, float eta, 
   if (ratings_out) *ratings_out = 0;
   return c->opt_file_decode ? epoch_from_file_device(c, path, eta, lambda, gb, mode, tile_ratings, ratings_out)
                             : epoch_from_file_host(c, path, eta, lambda, gb, mode, tile_ratings, ratings_out);
+}
+
+// SURVEY 8f-2, streaming ingest: one pass over the training file that leaves dataset `ds` finalized in HBM (like
+// mfb_dataset_load_file + mfb_dataset_finalize) with the records decoded on the GPU, and - with_epoch != 0 - runs the
+// SGD epoch on every chunk as it lands, so the first epoch costs what an out-of-core epoch costs and the parse + upload
+// stall is gone.  The dataset must be new (nothing appended).  Not for contexts with the dpmf arrays enabled (the
+// static logical clock is built from the host copy of the records: use mfb_dataset_load_file there).
+extern "C" int mfb_dataset_ingest_file(mfb_ctx* h, int ds, const char* path, int with_epoch, float eta, float lambda,
+                                       float gb, int mode, int64_t tile_ratings, int64_t* ratings_out) {
+  MFB_REQUIRE(h && path, "NULL argument");
+  MFB_REQUIRE(mode == MFB_MODE_HOGWILD || mode == MFB_MODE_ORDERED || mode == MFB_MODE_ATOMIC, "bad mode %d", mode);
+  Context* c = &h->c;
+  MFB_REQUIRE(ds >= 0 && ds < (int)c->datasets.size() && c->datasets[ds].used, "bad dataset id %d", ds);
+  Dataset* d = &c->datasets[ds];
+  MFB_REQUIRE(!d->finalized && d->h_run_uid.empty() && d->h_vid.empty(), "dataset %d is not empty", ds);
+  MFB_REQUIRE(!c->arr[MFB_UR], "dpmf is enabled on this context: its logical clock needs mfb_dataset_load_file");
+  MFB_CUDA(cudaSetDevice(c->device));
+  if (tile_ratings <= 0) tile_ratings = (int64_t)8 << 20;
+  tile_ratings = std::max<int64_t>(tile_ratings, 1024);
+  if (ratings_out) *ratings_out = 0;
+  struct stat st;
+  if (stat(path, &st) != 0) {
+    set_error("cannot open %s", path);
+    return MFB_E_IO;
+  }
+  if (st.st_size == 0) {  // an empty file is an empty dataset
+    d->h_run_off.assign(1, 0);
+    d->h_block_off.assign(1, 0);
+    MFB_CUDA(cudaMalloc(&d->d_run_off, sizeof(int32_t)));
+    MFB_CUDA(cudaMemset(d->d_run_off, 0, sizeof(int32_t)));
+    d->finalized = true;
+    return MFB_OK;
+  }
+  return epoch_from_file_device(c, path, eta, lambda, gb, mode, tile_ratings, ratings_out, d, with_epoch != 0);
 }

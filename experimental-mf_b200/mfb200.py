@@ -88,6 +88,8 @@ SIGNATURES = {
     "mfb_blocks_split_by_item": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(C.c_void_p)]),
     "mfb_blocks_merge_runs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "mfb_blocks_regroup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mfb_dataset_ingest_file": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                          C.c_int64, C.POINTER(C.c_int64)]),
     "mfb_wire_index_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mfb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -398,6 +400,16 @@ class Context:
         _check(lib().mfb_dataset_load_file(self.h, ds, path.encode()))
         _check(lib().mfb_dataset_finalize(self.h, ds))
         return ds.value
+
+    def dataset_ingest_file(self, path, with_epoch=False, eta=0.0, lam=0.0, gb=0.0, mode=MODE_ATOMIC, tile_ratings=0):
+        """streaming ingest: a finalized dataset from the file in one pass (records decoded on the GPU), optionally with
+        the SGD epoch run on every chunk as it lands; returns (dataset id, records)"""
+        ds = C.c_int()
+        _check(lib().mfb_dataset_create(self.h, C.byref(ds)))
+        n = C.c_int64()
+        _check(lib().mfb_dataset_ingest_file(self.h, ds.value, path.encode(), int(with_epoch), eta, lam, gb, mode, tile_ratings,
+                                             C.byref(n)))
+        return ds.value, n.value
 
     def dataset_free(self, ds):
         _check(lib().mfb_dataset_free(self.h, ds))

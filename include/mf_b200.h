@@ -188,6 +188,13 @@ int mfb_sgd_epoch_from_host(mfb_ctx* ctx, int ds, const mfb_blocks* src, float e
  * one have been applied.  *ratings (optional) = records processed. */
 int mfb_sgd_epoch_from_file(mfb_ctx* ctx, const char* path, float eta, float lambda, float gb, int mode,
                             int64_t tile_ratings, int64_t* ratings);
+/* Streaming ingest: ONE pass over the training file that leaves the new dataset `ds` finalized in HBM -
+ * what mfb_dataset_load_file + mfb_dataset_finalize do, with the records decoded on the GPU - and, with_epoch != 0, runs
+ * the SGD epoch on every chunk as it lands: the first epoch costs what an out-of-core epoch costs and the one-time parse
+ * + upload stall is gone (the reference overlaps read, parse and update the same way, main.cc:45-50).  ORDERED mode:
+ * bit-exact with load + finalize + mfb_sgd_epoch.  Not for contexts with MFB_ENABLE dpmf arrays (logical clock). */
+int mfb_dataset_ingest_file(mfb_ctx* ctx, int ds, const char* path, int with_epoch, float eta, float lambda, float gb,
+                            int mode, int64_t tile_ratings, int64_t* ratings);
 /* the host half of that path alone (no GPU): frames of the file, serialized mf.User messages in them (top-level walk of
  * every Block, blocks.proto:14-16) and the bytes inside those messages; MFB_E_IO on a truncated frame / malformed Block */
 int mfb_wire_index_file(const char* path, int64_t* nframes, int64_t* nusers, int64_t* user_bytes);

@@ -67,6 +67,77 @@ def test_file_epoch_larger_than_the_tile_buffers_equals_resident_epoch_on_confli
     c2.close()
 
 
+@pytest.mark.parametrize("with_epoch", [True, False], ids=["ingest fused with epoch 1", "ingest only"])
+def test_streaming_ingest_leaves_the_dataset_the_loader_builds(tmp_path, with_epoch):
+    """mfb_dataset_ingest_file: one pass over the file, records decoded on the GPU, chunks appended to the
+    resident tiles behind their update kernels.  Ordered schedule: the fused first epoch + a resident second epoch ==
+    load + finalize + two resident epochs == the oracle, bit for bit; same run / record / Block counts, same Block
+    boundaries (an epoch over a Block range), same SSE."""
+    nu, nv, dim = 400, 150, 32
+    tr, te, _ = mb.generate(mb.gen_params(nu, nv, 30000, test_frac=0.1, users_per_block=20))
+    path = tr.write(str(tmp_path / "train.bin"))
+    train = ol.Dataset(tr.block_off, tr.run_uid, tr.run_off, tr.vid, tr.rating)
+    m = ol.Model(nu, nv, dim, seed=4)
+    c1, c2 = ctx_from_model(m), ctx_from_model(m)
+    e1, e2 = mb.seteta(2e-2, 1, 1.0), mb.seteta(2e-2, 2, 1.0)
+    d1, n = c1.dataset_ingest_file(path, with_epoch, e1, 5e-3, GB, mb.MODE_ORDERED, tile_ratings=2000)
+    assert n == tr.nratings
+    if not with_epoch:
+        c1.sgd_epoch(d1, e1, 5e-3, GB, mb.MODE_ORDERED)
+    d2 = c2.dataset_from_file(path)
+    c2.sgd_epoch(d2, e1, 5e-3, GB, mb.MODE_ORDERED)
+    assert (c1.num_ratings(d1), c1.num_runs(d1), c1.num_blocks(d1)) == (c2.num_ratings(d2), c2.num_runs(d2), c2.num_blocks(d2))
+    assert (c1.num_ratings(d1), c1.num_runs(d1), c1.num_blocks(d1)) == (tr.nratings, tr.nruns, tr.nblocks)
+    for c, d in ((c1, d1), (c2, d2)):
+        c.sgd_epoch(d, e2, 5e-3, GB, mb.MODE_ORDERED)
+        c.sgd_epoch_blocks(d, 3, 11, e2, 5e-3, GB, mb.MODE_ORDERED)   # Block boundaries
+    oracle_sgd(m, train, e1, 5e-3, GB)
+    oracle_sgd(m, train, e2, 5e-3, GB)
+    oracle_sgd(m, train.block_range(3, 11), e2, 5e-3, GB)
+    for a, b in zip(c1.get_factors(), c2.get_factors()):
+        np.testing.assert_array_equal(a, b)
+    assert model_equal(c1, m)
+    s1, s2 = c1.sse(d1, GB), c2.sse(d2, GB)
+    assert s1[1] == s2[1] and abs(s1[0] - s2[0]) <= 1e-12 * s2[0]   # (fp64 sums in the order the blocks finish)
+    c1.close()
+    c2.close()
+
+
+def test_streaming_ingest_in_the_production_schedule_and_its_refusals(tmp_path):
+    """conflict-free data (the order cannot matter): ingest fused with the first epoch == resident epoch == oracle
+    to 1e-5; a dpmf context, a non-empty dataset and a damaged file are refused, and the context stays usable"""
+    n, dim = 100_000, 64
+    rng = np.random.default_rng(3)
+    ds = ol.Dataset(np.r_[np.arange(0, n, 500), n], rng.permutation(n), np.arange(n + 1), rng.permutation(n),
+                    rng.integers(1, 6, n))
+    path = ds.write(str(tmp_path / "train.bin"))
+    m = ol.Model(n, n, dim, seed=6, scale=0.3)
+    c1, c2 = ctx_from_model(m), ctx_from_model(m)
+    d1, got = c1.dataset_ingest_file(path, True, 0.05, 0.02, GB, mb.MODE_ATOMIC, tile_ratings=8000)
+    assert got == n
+    d2 = c2.dataset_from_file(path)
+    for c, d, first in ((c1, d1, False), (c2, d2, True)):
+        if first:
+            c.sgd_epoch(d, 0.05, 0.02, GB, mb.MODE_ATOMIC)
+        c.sgd_epoch(d, 0.03, 0.02, GB, mb.MODE_ATOMIC)
+    oracle_sgd(m, ds, 0.05, 0.02, GB)
+    oracle_sgd(m, ds, 0.03, 0.02, GB)
+    assert model_rel_err(c1, m) <= 1e-5 and model_rel_err(c2, m) <= 1e-5
+    # refusals
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(open(path, "rb").read()[:-7])
+    with pytest.raises(mb.MfbError):
+        c1.dataset_ingest_file(str(bad))
+    d3, got3 = c1.dataset_ingest_file(path)          # ... and the context still ingests
+    assert got3 == n and c1.num_runs(d3) == n
+    c3 = mb.Context(50, 50, 16)
+    c3.enable(2)
+    with pytest.raises(mb.MfbError):
+        c3.dataset_ingest_file(path)
+    for c in (c1, c2, c3):
+        c.close()
+
+
 def _varint(v):
     out = bytearray()
     while v >= 0x80:
