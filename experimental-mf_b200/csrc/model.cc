@@ -107,9 +107,21 @@ void MF::seteta(int round) { eta_ = mfb_seteta(eta0_, round, gam_); }  // model.
 
 int MF::schedule() const { return data_in_fly_ <= 1 ? MFB_MODE_ORDERED : MFB_MODE_ATOMIC; }
 
+// MF_STREAM_INGEST=0: parse the training file on the host cores and upload it (mfb_dataset_load_file + finalize);
+// default: one streaming pass with the records decoded on the GPU (mfb_dataset_ingest_file), which run(MF&) fuses
+// with the first epoch - the reference overlaps read, parse and update the same way (main.cc:45-50)
+static bool stream_ingest() {
+  const char* e = getenv("MF_STREAM_INGEST");
+  return !e || atoi(e) != 0;
+}
+
 void MF::load_train() {
   if (train_ds_ >= 0) return;
   check(mfb_dataset_create(ctx_, &train_ds_), "mfb_dataset_create");
+  if (stream_ingest() && !needs_host_records()) {
+    check(mfb_dataset_ingest_file(ctx_, train_ds_, train_data_, 0, 0.f, 0.f, gb_, schedule(), 0, nullptr), "ingest training file");
+    return;
+  }
   check(mfb_dataset_load_file(ctx_, train_ds_, train_data_), "load training file");
   check(mfb_dataset_finalize(ctx_, train_ds_), "mfb_dataset_finalize");
 }
@@ -148,6 +160,14 @@ void MF::sgd_epoch() {
           "mfb_sgd_epoch_from_file");
     return;
   }
+  if (train_ds_ < 0 && stream_ingest() && !needs_host_records()) {
+    // the first epoch of the run: ingest and update in one pass over the file
+    check(mfb_dataset_create(ctx_, &train_ds_), "mfb_dataset_create");
+    check(mfb_dataset_ingest_file(ctx_, train_ds_, train_data_, 1, eta_, lambda_, gb_, schedule(), 0, nullptr),
+          "ingest training file + first epoch");
+    return;
+  }
+  load_train();
   check(mfb_sgd_epoch(ctx_, train_ds_, eta_, lambda_, gb_, schedule()), "mfb_sgd_epoch");
 }
 
@@ -517,7 +537,7 @@ void run(MF& mf) {
   mf::Blocks blocks_test;
   plain_read(mf.test_data_, blocks_test);
   lap("test file");
-  if (tile_ratings() <= 0) mf.load_train();
+  if (tile_ratings() <= 0 && !stream_ingest()) mf.load_train();  // (default: ingested by the first epoch itself)
   lap("training file (parse, ingest)");
   s = Time::now();
   for (int iter = mf.start_round_ + 1; iter <= mf.iter_; iter++) {  // (a model loaded with its .state continues)

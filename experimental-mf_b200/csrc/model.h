@@ -80,6 +80,7 @@ class MF {
   void pull();            // HBM -> theta_/phi_/bu_/bv_
   void push();            // theta_/phi_/bu_/bv_ -> HBM
   void load_train();      // one-time ingest of train_data_
+  virtual bool needs_host_records() const { return false; }  // DPMF: its logical clock is built from the host copy
   int schedule() const;   // MFB_MODE_ORDERED for --fly 1, else the parallel schedule
   void sgd_epoch();       // SgdFilter over the whole file with the current eta_
   int dataset_of(const mf::Blocks& blocks);
@@ -117,6 +118,7 @@ class DPMF : public MF {
   int round_;
   void sgld_epoch();      // SgldFilter over the whole file
   mfb_sgld_params params() const;
+  bool needs_host_records() const override { return true; }
 };
 
 class AdaptRegMF : public MF {

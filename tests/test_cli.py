@@ -71,10 +71,12 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_mf_single_thread_order_prints_reference_numbers(tmp_path):
+@pytest.mark.parametrize("stream_ingest", ["1", "0"], ids=["ingest fused with epoch 1", "host parse + upload"])
+def test_cli_mf_single_thread_order_prints_reference_numbers(tmp_path, stream_ingest):
     """./mf --alg mf --fly 1 --model <seeded> : same command line for the reference binary and for
     ours; the per-epoch tRMSE lines must agree to the printed precision, and the checkpoint written
-    by save_model must hold the oracle's factors bit for bit."""
+    by save_model must hold the oracle's factors bit for bit.  Both ways of getting the training file
+    into HBM: the streaming ingest fused with the first epoch (default) and MF_STREAM_INGEST=0."""
     nu, nv, dim = 300, 120, 32
     train, test, _ = ol.make_ratings(nu, nv, 9000, seed=5)
     tp, sp = train.write(str(tmp_path / "train")), test.write(str(tmp_path / "test"))
@@ -85,7 +87,7 @@ def test_cli_mf_single_thread_order_prints_reference_numbers(tmp_path):
     args = ["--alg", "mf", "--train", tp, "--test", sp, "--nu", nu, "--nv", nv, "--dim", dim, "--iter", 3,
             "--fly", 1, "--eta", eta0, "--lambda", lam, "--gam", gam, "--bias", GB, "--model", mp,
             "--result", str(tmp_path / "out")]
-    got = run(MF, *args, env=dict(os.environ, MF_SAVE_EVERY="3"))
+    got = run(MF, *args, env=dict(os.environ, MF_SAVE_EVERY="3", MF_STREAM_INGEST=stream_ingest))
     assert got.returncode == 0, got.stderr
     lines = got.stdout.strip().splitlines()
     assert len(lines) == 3 and all(re.fullmatch(r"iter#\d+\t[0-9.]+\ttRMSE=[0-9.]+", l) for l in lines)
