@@ -693,10 +693,24 @@ def run_b200_arm(args, wl):
             c.set_option("file_decode", 0)
             best_host, h2d_h, _ = file_epochs(2)
             c.set_option("file_decode", 1)
+            # streaming ingest: the same pass over the file that also leaves a finalized, resident dataset behind
+            ingest = None
+            try:
+                epoch[0] += 1
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ds_i, n_i = c.dataset_ingest_file(fp, True, mb.seteta(ETA0, epoch[0], GAM), LAMBDA, GB, mode, args.tile)
+                c.sync()
+                ingest = {"ms": 1e3 * (time.perf_counter() - t0), "ratings": n_i, "runs": c.num_runs(ds_i),
+                          "what": "mfb_dataset_ingest_file with the epoch fused: file -> finalized resident dataset + one SGD epoch, "
+                                  "one pass (the mf driver's default way in); compare ingest_s (host arrays -> HBM) + an epoch"}
+                c.dataset_free(ds_i)
+            except Exception as e:
+                ingest = {"error": "%s: %s" % (type(e).__name__, e)}
             from_file = {"value": ntrain / best, "unit": UNIT, "ms_per_step": 1e3 * best, "file_bytes": fbytes,
                          "file_gb_per_s": fbytes / best / 1e9,
                          "h2d_bytes_per_step": h2d_f, "tile_ratings": args.tile or (8 << 20), "host_cores": cores,
-                         "test_rmse": rmse_f,
+                         "test_rmse": rmse_f, "streaming_ingest": ingest,
                          "host_decode": {"value": ntrain / best_host, "ms_per_step": 1e3 * best_host, "h2d_bytes_per_step": h2d_h,
                                          "what": "option file_decode = 0: frames decoded by the host cores into pinned SoA chunks "
                                                  "(the round's first version of this path)"},
